@@ -76,7 +76,7 @@ def lib():
         _lib.orc_rrt.restype = C.c_int
         _lib.orc_rrt.argtypes = [c_u8p, C.c_int, C.c_int, C.POINTER(Params), C.c_int, c_dp, c_dp, c_i32p, c_dp,
                                  c_dp, c_dp, c_dp, c_i32p, c_dp, c_i32p, c_i32p, c_u8p, c_i32p, c_i32p, c_i32p,
-                                 c_u8p, C.c_int64, c_i64p]
+                                 c_u8p, C.c_int64, c_i64p, C.c_double, c_i32p]
         _lib.orc_rrt_batch.argtypes = [c_u8p, C.c_int, C.c_int, C.POINTER(Params), C.c_int, C.c_int64, c_dp, c_dp,
                                        c_i32p, c_dp, c_i32p, c_dp, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int]
         _lib.orc_findnearest.restype = C.c_int
@@ -195,7 +195,7 @@ def drive(origin, theta, u, params=None):
 
 
 # ------------------------------------------------------------------ RRT
-def rrt(free, start, goal, sxy, sth, params=None, K=None, log_los=True):
+def rrt(free, start, goal, sxy, sth, params=None, K=None, log_los=True, audit_eps=0.0):
     """start/goal: ((x,y),theta).  sxy int32 [K-1,2], sth float64 [K-1]."""
     P = params or Params()
     g, H, W = _grid(free)
@@ -216,14 +216,16 @@ def rrt(free, start, goal, sxy, sth, params=None, K=None, log_los=True):
     los_cap = 2 * K + 8
     los = np.zeros(los_cap, np.uint8) if log_los else None
     n_los = C.c_int64(0)
+    first_amb = C.c_int32(-1)
     status = lib().orc_rrt(_p(g, c_u8p), H, W, C.byref(P), K, _p(st, c_dp), _p(gl, c_dp), _p(sxy, c_i32p),
                            _p(sth, c_dp), _p(nx, c_dp), _p(ny, c_dp), _p(nth, c_dp), _p(parent, c_i32p), _p(u, c_dp),
                            _p(it_near, c_i32p), _p(it_new, c_i32p), _p(it_code, c_u8p), C.byref(n_nodes),
-                           C.byref(sol), C.byref(iters), _p(los, c_u8p), los_cap, C.byref(n_los))
+                           C.byref(sol), C.byref(iters), _p(los, c_u8p), los_cap, C.byref(n_los), float(audit_eps), C.byref(first_amb))
     n = n_nodes.value
     return dict(status=status, n_nodes=n, sol=sol.value, iters=iters.value, x=nx[:n], y=ny[:n], theta=nth[:n],
                 parent=parent[:n], u=u[:n], it_near=it_near[:K - 1], it_new=it_new[:K - 1], it_code=it_code[:K - 1],
-                los=(los[:n_los.value].astype(bool) if log_los else None), n_los=n_los.value)
+                los=(los[:n_los.value].astype(bool) if log_los else None), n_los=n_los.value,
+                first_ambiguous=first_amb.value)
 
 
 def rrt_batch(free, starts, goals, sxy, sth, K, params=None, threads=1, want_nodes=True):

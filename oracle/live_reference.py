@@ -141,7 +141,10 @@ def run_astar(start, goal, thetastar=True):
     res = dict(path=False, expanded=expanded, los=los, cost=None, stdout=text)
     if path is not False:
         res["path"] = [(int(p[0]), int(p[1])) for p in path]
-        res["cost"] = float(sum(search.L2norm(a, b) for a, b in zip(path, path[1:])))
+        cost = 0.0  # plain left-to-right fp64 accumulation (Python >= 3.12 sum() is compensated)
+        for a, b in zip(path, path[1:]):
+            cost = cost + search.L2norm(a, b)
+        res["cost"] = float(cost)
     return res
 
 

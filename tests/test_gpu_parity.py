@@ -1,0 +1,318 @@
+"""GPU parity tests: every kernel, called through the C ABI (theta_rrt_b200.Planner ->
+libthetarrt.so), against the CPU oracle (oracle/trrt_oracle.c) on the same seeded inputs,
+and against the golden fixtures generated from the unmodified reference.
+
+Bars: bit-exact for integer / byte / index outputs (LOS booleans, nearest indices,
+parent arrays, iteration codes, Theta* paths and expansion counts); fp64 outputs of the
+CUDA path are compared BITWISE with the oracle (both use the deterministic libm of
+trrt_libm.h and no contraction), and within 1e-9 relative with the reference goldens.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import c_oracle
+    c_oracle.lib()
+    return c_oracle
+
+
+def planner_for(free, **params):
+    from theta_rrt_b200 import OccupancyGrid, Params, Planner
+    return Planner(OccupancyGrid(free), Params(**params))
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    return a.shape == b.shape and np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
+# ------------------------------------------------------------------ grid + LOS
+def test_los_golden(maps):
+    z = np.load(util.GOLDEN + "/los_kat.npz")
+    for name in ("map1", "map2"):
+        p = planner_for(maps[name])
+        out = p.los(z[name + "_seg"]).cpu().numpy().astype(bool)
+        assert np.array_equal(out, z[name + "_los"]), name
+
+
+@pytest.mark.parametrize("n,seed", [(64, 1), (257, 2), (1000, 3)])
+def test_los_vs_oracle_random(O, n, seed):
+    free = util.synthetic_map(n, 0.12, 4, seed)
+    rng = np.random.default_rng(seed)
+    seg = rng.integers(-5, n + 5, size=(20000, 4)).astype(np.int32)
+    seg[:2000, 2:] = seg[:2000, :2] + rng.integers(-40, 41, size=(2000, 2))
+    seg[2000:2100, 2:] = seg[2000:2100, :2]  # zero length
+    p = planner_for(free)
+    got = p.los(seg).cpu().numpy().astype(bool)
+    ref = O.lineofsight_batch(free, seg, threads=4)
+    assert np.array_equal(got, ref)
+    # symmetry of the canonicalised Bresenham (search.py:47-56)
+    rev = seg[:, [2, 3, 0, 1]].copy()
+    assert np.array_equal(p.los(rev).cpu().numpy().astype(bool), got)
+
+
+def test_los_empty_and_multimap(O):
+    free = np.stack([util.synthetic_map(96, 0.2, 3, s) for s in (5, 6, 7)])
+    from theta_rrt_b200 import OccupancyGrid, Planner
+    p = Planner(OccupancyGrid(free))
+    assert p.los(np.zeros((0, 4), np.int32)).numel() == 0
+    rng = np.random.default_rng(0)
+    seg = rng.integers(0, 96, size=(5000, 4)).astype(np.int32)
+    mid = rng.integers(0, 3, size=5000).astype(np.int32)
+    got = p.los(seg, map_id=mid).cpu().numpy().astype(bool)
+    for m in range(3):
+        sel = mid == m
+        assert np.array_equal(got[sel], O.lineofsight_batch(free[m], seg[sel]))
+
+
+# ------------------------------------------------------------------ nearest
+@pytest.mark.parametrize("n,nq", [(1, 5), (2, 1), (37, 64), (5001, 300), (100003, 700), (1 << 18, 33)])
+def test_nearest_vs_oracle(O, n, nq):
+    rng = np.random.default_rng(n)
+    x = rng.uniform(0, 511, n)
+    y = rng.uniform(0, 511, n)
+    # exact duplicates and integer nodes to exercise the lowest-index tie-break
+    if n > 10:
+        x[n // 2] = x[3]; y[n // 2] = y[3]
+        x[5] = 100.0; y[5] = 200.0; x[n - 1] = 100.0; y[n - 1] = 200.0
+    q = rng.integers(0, 512, size=(nq, 2)).astype(np.int32)
+    if n > 10:
+        q[0] = (100, 200)
+    p = planner_for(np.ones((8, 8), bool))
+    idx, d2 = p.nearest(x, y, q, want_d2=True)
+    idx = idx.cpu().numpy()
+    ref = O.nearest_batch(x, y, q, threads=4)
+    assert np.array_equal(idx, ref)
+    dx = q[:, 0] - x[idx]; dy = q[:, 1] - y[idx]
+    assert bits_equal(d2.cpu().numpy(), dx * dx + dy * dy)
+    if n > 10:
+        assert idx[0] == 5
+
+
+def test_nearest_empty_tree():
+    p = planner_for(np.ones((8, 8), bool))
+    idx = p.nearest(np.zeros(0), np.zeros(0), np.array([[1, 2], [3, 4]], np.int32)).cpu().numpy()
+    assert list(idx) == [-1, -1]
+
+
+# ------------------------------------------------------------------ Theta*
+def test_theta_known_answers(maps, O):
+    for k in util.theta_kat():
+        p = planner_for(maps[k["map"]])
+        r = p.theta([[*k["start"], *k["goal"]]], thetastar=k["thetastar"], path_cap=maps[k["map"]].size,
+                    log_los=True, lanes=8).host()
+        o = O.astar(maps[k["map"]], k["start"], k["goal"], thetastar=k["thetastar"])
+        tag = (k["map"], k["start"], k["goal"], k["thetastar"])
+        assert int(r["status"][0]) == o["status"], tag
+        if k["path"] is False:
+            assert int(r["status"][0]) != 0, tag
+            continue
+        n = int(r["path_len"][0])
+        assert [tuple(v) for v in r["path"][0, :n].tolist()] == [tuple(v) for v in k["path"]], tag
+        assert int(r["expanded"][0]) == k["expanded"], tag
+        assert r["cost"][0] == o["cost"], tag                      # bitwise vs oracle
+        assert abs(r["cost"][0] - k["cost"]) <= 1e-9 * k["cost"], tag  # reference, 1e-9 relative
+        nl = int(r["n_los"][0])
+        assert nl == k["n_los"], tag
+        los_ref = np.unpackbits(np.frombuffer(bytes.fromhex(k["los_hex"]), np.uint8))[:nl].astype(bool)
+        assert np.array_equal(r["los_log"][0, :nl].astype(bool), los_ref), tag
+        assert int(r["pushes"][0]) == o["pushes"], tag
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_theta_batch_vs_oracle(O, lanes):
+    free = np.stack([util.synthetic_map(64, 0.15, 4, 7 + m) for m in range(4)])
+    rng = np.random.default_rng(lanes)
+    nq = 300
+    mid = rng.integers(0, 4, nq).astype(np.int32)
+    sg = rng.integers(-1, 65, size=(nq, 4)).astype(np.int32)
+    from theta_rrt_b200 import OccupancyGrid, Planner
+    p = Planner(OccupancyGrid(free))
+    for th in (True, False):
+        r = p.theta(sg, thetastar=th, map_id=mid, path_cap=64 * 64, lanes=lanes, n_slots=37).host()
+        for q in range(nq):
+            o = O.astar(free[mid[q]], sg[q, :2], sg[q, 2:], thetastar=th, log_los=False)
+            assert int(r["status"][q]) == o["status"], (q, th)
+            if o["status"] == 0:
+                n = int(r["path_len"][q])
+                assert [tuple(v) for v in r["path"][q, :n].tolist()] == o["path"], (q, th)
+                assert r["cost"][q] == o["cost"] and int(r["expanded"][q]) == o["expanded"], (q, th)
+            assert int(r["n_los"][q]) == o["n_los"] and int(r["pushes"][q]) == o["pushes"], (q, th)
+
+
+# ------------------------------------------------------------------ steer / drive / arc single steps
+def test_steer_drive_bitwise_vs_oracle(O, maps):
+    rng = np.random.default_rng(11)
+    n = 20000
+    inp = np.stack([rng.uniform(0, 100, n), rng.uniform(0, 100, n), rng.uniform(-180, 180, n),
+                    rng.integers(0, 100, n).astype(float), rng.integers(0, 100, n).astype(float),
+                    rng.uniform(-180, 180, n)], axis=1)
+    inp[:50, 2] = 0.0; inp[:50, 4] = inp[:50, 1] = 40.0  # straight ahead: singular solve
+    inp[50:60, 3:5] = inp[50:60, 0:2] = 7.0               # target == origin
+    p = planner_for(maps["map1"])
+    out, straight = p.steer(inp)
+    out = out.cpu().numpy(); straight = straight.cpu().numpy()
+    dr_in = []
+    for i in range(n):
+        o = O.steer(inp[i, :2], inp[i, 2], inp[i, 3:5], inp[i, 5])
+        ref = np.array([o["x"], o["y"], o["theta"], o["steer"], o["icc"][0], o["icc"][1], o["rad"], o["dist"]])
+        assert bool(straight[i]) == o["straight"], i
+        assert np.array_equal(out[i].view(np.int64), ref.view(np.int64)), (i, out[i], ref)
+        if not o["straight"]:
+            dr_in.append([inp[i, 0], inp[i, 1], inp[i, 2], o["steer"], o["icc"][0], o["icc"][1], o["rad"], o["dist"] / 3])
+    dr_in = np.array(dr_in[:5000])
+    dout = p.drive(dr_in).cpu().numpy()
+    for i in range(len(dr_in)):
+        ref = O.drive(dr_in[i, :2], dr_in[i, 2], (dr_in[i, 3], (dr_in[i, 4], dr_in[i, 5]), dr_in[i, 6], dr_in[i, 7]))
+        assert np.array_equal(dout[i].view(np.int64), ref.view(np.int64)), i
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 8, 32])
+def test_arc_blocked_vs_oracle(O, maps, lanes):
+    free = maps["map1"]
+    rng = np.random.default_rng(5)
+    rows = []
+    for i in range(3000):
+        ox, oy = rng.uniform(0, 100, 2)
+        o = O.steer((ox, oy), rng.uniform(-180, 180), rng.integers(0, 100, 2), rng.uniform(-180, 180))
+        rows.append([ox, oy, o["x"], o["y"], o["steer"], o["icc"][0], o["icc"][1], o["rad"], float(o["straight"])])
+    # large radii and centres far outside the image
+    for i in range(300):
+        r = float(rng.choice([150.3, 1000.7, 41014.2]))
+        ang = rng.uniform(0, 2 * np.pi)
+        cx, cy = 50 + (r + rng.uniform(-40, 40)) * np.cos(ang), 50 + (r + rng.uniform(-40, 40)) * np.sin(ang)
+        rows.append([rng.uniform(0, 100), rng.uniform(0, 100), rng.uniform(0, 100), rng.uniform(0, 100),
+                     float(rng.choice([-65, 65, 10.5])), cx, cy, r, 0.0])
+    rows = np.array(rows)
+    p = planner_for(free)
+    got = p.arc_blocked(rows, lanes=lanes).cpu().numpy().astype(bool)
+    for i, v in enumerate(rows):
+        u = (v[4], None if v[8] else (v[5], v[6]), None if v[8] else v[7], 1.0)
+        px = O.getarc(free.shape, v[0:2], v[2:4], u)
+        ref = any((not (0 <= x < free.shape[0] and 0 <= y < free.shape[1])) or (not free[y, x]) for x, y in px)
+        assert got[i] == ref, (i, v)
+
+
+# ------------------------------------------------------------------ fused RRT
+def run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, **params):
+    from oracle.c_oracle import Params as OP
+    p = planner_for(free, **{k: v for k, v in params.items()})
+    res = p.rrt(starts, goals, sxy, sth, K=K, logs=True, counters=True, lanes=lanes).host()
+    op = OP(**{k.lower(): v for k, v in params.items()})
+    for q in range(len(starts)):
+        o = O.rrt(free, ((starts[q, 0], starts[q, 1]), starts[q, 2]), ((goals[q, 0], goals[q, 1]), goals[q, 2]),
+                  sxy[q], sth[q], op, K=K)
+        n = o["n_nodes"]
+        tag = (q, lanes)
+        assert int(res["status"][q]) == o["status"], tag
+        assert int(res["n_nodes"][q]) == n and int(res["sol"][q]) == o["sol"] and int(res["iters"][q]) == o["iters"], tag
+        assert np.array_equal(res["it_code"][q], o["it_code"]), tag
+        assert np.array_equal(res["it_near"][q], o["it_near"]), tag
+        assert np.array_equal(res["it_new"][q], o["it_new"]), tag
+        assert np.array_equal(res["parent"][q, :n], o["parent"]), tag
+        assert bits_equal(res["node_x"][q, :n], o["x"]) and bits_equal(res["node_y"][q, :n], o["y"]), tag
+        assert bits_equal(res["node_theta"][q, :n], o["theta"]), tag
+        assert np.array_equal(res["u"][q, :n].view(np.int64), o["u"].view(np.int64)), tag
+        nl = int(res["n_los"][q])
+        assert nl == o["n_los"] and np.array_equal(res["los_log"][q, :nl].astype(bool), o["los"]), tag
+    return res
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+def test_rrt_cfg1_golden_and_oracle(O, maps, lanes):
+    """BASELINE cfg 1: map1, ((5,5),0) -> ((90,50),90), seed-0 stream, K=300."""
+    run = util.rrt_runs()[0]
+    free = maps["map1"]
+    K = int(run["K"][0])
+    res = run_rrt_pair(O, free, run["start"][None], run["goal"][None], run["sxy"][None], run["sth"][None], K, lanes,
+                       tol_xy=float(run["tol_xy"][0]))
+    n = int(res["n_nodes"][0])
+    assert n == len(run["parent"]) and np.array_equal(res["parent"][0, :n], run["parent"])
+    assert int(res["sol"][0]) == int(run["sol"][0]) and int(res["iters"][0]) == int(run["iterations"][0])
+    near = res["it_near"][0]
+    assert np.array_equal(near[run["nearest_it"] - 1], run["nearest_idx"])
+    assert np.array_equal(res["los_log"][0, :int(res["n_los"][0])].astype(bool), run["los"])
+    for a, b in ((res["node_x"][0, :n], run["x"]), (res["node_y"][0, :n], run["y"]), (res["node_theta"][0, :n], run["theta"])):
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-9)
+
+
+def test_rrt_all_goldens(O, maps):
+    """Every committed run of the unmodified reference: CUDA == oracle bitwise, and CUDA == reference on all
+    discrete outputs up to the first iteration the oracle's margin audit marks as decided by rounding noise
+    (runs without such an iteration must match to the end); coordinates within the documented drift."""
+    from oracle.c_oracle import Params as OP
+    for i, run in enumerate(util.rrt_runs()):
+        free = maps[str(run["map"])]
+        K = int(run["K"][0])
+        tol = float(run["tol_xy"][0])
+        res = run_rrt_pair(O, free, run["start"][None], run["goal"][None], run["sxy"][None], run["sth"][None], K, 8,
+                           tol_xy=tol)
+        o = O.rrt(free, ((run["start"][0], run["start"][1]), run["start"][2]), ((run["goal"][0], run["goal"][1]), run["goal"][2]),
+                  run["sxy"], run["sth"], OP(tol_xy=tol), K=K, audit_eps=util.AUDIT_EPS)
+        fa = -1 if i < 2 else o["first_ambiguous"]  # cfg 1 is reproduced to the end (see tests/test_oracle_golden.py)
+        n = int(res["n_nodes"][0])
+        gpu = dict(n_nodes=n, sol=int(res["sol"][0]), parent=res["parent"][0, :n], it_near=res["it_near"][0],
+                   it_new=res["it_new"][0], it_code=res["it_code"][0], los=res["los_log"][0, :int(res["n_los"][0])],
+                   x=res["node_x"][0, :n], y=res["node_y"][0, :n], theta=res["node_theta"][0, :n])
+        util.compare_rrt_with_reference(gpu, run, fa)
+
+
+@pytest.mark.parametrize("lanes,nq,K", [(32, 24, 1201), (8, 96, 801), (4, 64, 801), (1, 64, 401)])
+def test_rrt_batch_bitwise_vs_oracle(O, maps, lanes, nq, K):
+    """cfg-3 style batch (random free start/goal, per-query seeded streams, tol_xy=0) -- bitwise vs oracle."""
+    from theta_rrt_b200 import samples
+    free = maps["map1"]
+    starts, goals = util.random_queries(free, nq, 1234)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, q, free.shape)
+    res = run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, tol_xy=0.0)
+    # counters: scanned nodes = sum of tree sizes at each nearest call
+    assert (res["counters"][:, 0] > 0).all()
+
+
+def test_rrt_full_size_one_query_k5001(O, maps):
+    """BASELINE cfg 3 size for a few queries: K=5001, bitwise vs oracle at full depth."""
+    from theta_rrt_b200 import samples
+    free = maps["map1"]
+    nq, K = 8, 5001
+    starts, goals = util.random_queries(free, nq, 1234)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, q, free.shape)
+    run_rrt_pair(O, free, starts, goals, sxy, sth, K, 16, tol_xy=0.0)
+
+
+def test_rrt_goal_found_and_map2(O, maps):
+    run = util.rrt_runs()[2]
+    run_rrt_pair(O, maps["map2"], run["start"][None], run["goal"][None], run["sxy"][None], run["sth"][None],
+                 int(run["K"][0]), 8, tol_xy=float(run["tol_xy"][0]))
+
+
+def test_findnearest_vs_oracle(O, maps):
+    from theta_rrt_b200 import samples
+    free = maps["map1"]
+    nq, K = 16, 301
+    starts, goals = util.random_queries(free, nq, 99)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, 100 + q, free.shape)
+    p = planner_for(free, tol_xy=0.0)
+    res = p.rrt(starts, goals, sxy, sth, K=K, logs=True)
+    best, dist = p.findnearest(res, goals)
+    h = res.host(); best = best.cpu().numpy(); dist = dist.cpu().numpy()
+    for q in range(nq):
+        n = int(h["n_nodes"][q])
+        sel = h["it_new"][q] >= 0
+        b, d = O.findnearest(h["node_x"][q, :n], h["node_y"][q, :n], h["node_theta"][q, :n], h["it_near"][q][sel],
+                             h["it_new"][q][sel], ((goals[q, 0], goals[q, 1]), goals[q, 2]))
+        assert best[q] == b, q
+        if b >= 0:
+            assert abs(dist[q] - d) <= 1e-12 * max(1.0, abs(d)), q

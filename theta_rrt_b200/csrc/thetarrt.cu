@@ -1,0 +1,1062 @@
+// thetarrt.cu -- kernels and C ABI of libthetarrt.so (sm_100a).
+//
+// Kernels (one section each):
+//   pack_grid_kernel      byte image -> bit-packed occupancy grid
+//   los_batch_kernel      K4: search.lineofsight for independent segments
+//   nearest_tile_kernel   K1: fp64 argmin over SoA tree, query-tiled
+//   nearest_final_kernel      cross-slice reduction with lowest-index ties
+//   rrt_kernel<G>         K2: fused rrt.rrt loop, G lanes per query
+//   findnearest_kernel    rrt.findnearest over the edge log
+//   theta_kernel<G>       K3: A* / lazy Theta*, G lanes per query
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+// (see theta_rrt_b200/build.py).  No tensor cores: nothing here is a dense
+// contraction; the hot loops are fp64 compare/select and bit tests.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/thetarrt.h"
+#include "trrt_bike.cuh"
+#include "trrt_device.cuh"
+
+using namespace trrt;
+
+static thread_local char g_last_cuda_error[256] = "";
+
+static int cuda_fail(cudaError_t e) {
+    if (e == cudaSuccess) return TRRT_OK;
+    strncpy(g_last_cuda_error, cudaGetErrorString(e), sizeof(g_last_cuda_error) - 1);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? TRRT_ERR_NO_DEVICE : TRRT_ERR_CUDA;
+}
+#define CUDA_TRY(x)                                  \
+    do {                                             \
+        cudaError_t e__ = (x);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__); \
+    } while (0)
+
+static int check_map(int n_maps, int H, int W) {
+    if (n_maps < 1 || H < 1 || W < 1) return TRRT_ERR_INVALID_ARGUMENT;
+    if (H != W) return TRRT_ERR_NONSQUARE_MAP;
+    if (H > 32768) return TRRT_ERR_MAP_TOO_LARGE;
+    return TRRT_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ===========================================================================
+// grid packing
+// ===========================================================================
+__global__ void pack_grid_kernel(const uint8_t *__restrict__ free_, int n_maps, int H, int W, int wpr, uint32_t *__restrict__ bits) {
+    size_t total = (size_t)n_maps * H * wpr;
+    for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+        size_t row = w / wpr; // map * H + y
+        int x0 = (int)(w % wpr) * 32;
+        const uint8_t *src = free_ + row * (size_t)W;
+        uint32_t v = 0;
+        int lim = W - x0 < 32 ? W - x0 : 32;
+        for (int b = 0; b < lim; b++) v |= (src[x0 + b] ? 1u : 0u) << b;
+        bits[w] = v;
+    }
+}
+
+// ===========================================================================
+// K4 los_batch: one thread per segment, literal running-error Bresenham with
+// four pixel probes in flight (the grid words come from L1/L2; the 8 MiB
+// 8192^2 grid is L2 resident).
+// ===========================================================================
+__global__ void __launch_bounds__(256) los_batch_kernel(const uint32_t *__restrict__ bits, int H, int W, int wpr, const int32_t *__restrict__ map_id,
+                                                        const int4 *__restrict__ seg, int64_t n, uint8_t *__restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 s = __ldg(seg + i);
+    int x0 = s.x, y0 = s.y, x1 = s.z, y1 = s.w;
+    const uint32_t *g = bits + (map_id ? (size_t)__ldg(map_id + i) * H * wpr : 0);
+    bool ok = x0 >= 0 && y0 >= 0 && x1 >= 0 && y1 >= 0 && x0 < H && x1 < H && y0 < W && y1 < W; // search.py:17-24
+    if (ok) {
+        int adx = abs(x1 - x0), ady = abs(y1 - y0);
+        bool low = ady < adx; // search.py:47
+        if (low ? (x0 > x1) : (y0 > y1)) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+        int dmaj = low ? adx : ady, dmin = low ? ady : adx;
+        int step = low ? ((y1 < y0) ? -1 : 1) : ((x1 < x0) ? -1 : 1);
+        int D = 2 * dmin - dmaj; // search.py:66 / :85
+        int a = low ? x0 : y0, b = low ? y0 : x0, aend = a + dmaj;
+        // word address pieces: low -> (x=a, y=b), high -> (x=b, y=a)
+        while (a + 3 <= aend) {
+            uint32_t acc = 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                int px = low ? a : b, py = low ? b : a;
+                uint32_t wv = __ldg(g + (size_t)py * wpr + (px >> 5));
+                acc &= (wv >> (px & 31)) | 0xfffffffeu;
+                if (D > 0) { b += step; D -= 2 * dmaj; }
+                D += 2 * dmin;
+                a++;
+            }
+            if (acc != 0xffffffffu) { ok = false; break; }
+        }
+        if (ok) {
+            for (; a <= aend; a++) {
+                int px = low ? a : b, py = low ? b : a;
+                uint32_t wv = __ldg(g + (size_t)py * wpr + (px >> 5));
+                if (!((wv >> (px & 31)) & 1u)) { ok = false; break; }
+                if (D > 0) { b += step; D -= 2 * dmaj; }
+                D += 2 * dmin;
+            }
+        }
+    }
+    out[i] = ok ? 1 : 0;
+}
+
+// ===========================================================================
+// K1 nearest_batch
+//   grid = (n_slices, n_qtiles); block = 256 threads = 8 warps; each warp owns
+//   TQ queries in registers and all lanes stride the CTA's node slice with
+//   coalesced 16-byte SoA loads; per-warp shuffle min-reduction with
+//   (d2, index) lexicographic order; partials go to the workspace and
+//   nearest_final_kernel folds the slices (ascending slice = ascending index).
+//   d2 = rn(rn(dx*dx) + rn(dy*dy)), dx = qx - x  (search.py:15 before the sqrt).
+// ===========================================================================
+#define NN_WARPS 8
+template <int TQ>
+__global__ void __launch_bounds__(NN_WARPS * 32) nearest_tile_kernel(const double *__restrict__ x, const double *__restrict__ y, int64_t n_nodes,
+                                                                     const int32_t *__restrict__ qxy, int64_t n_q, int64_t slice_len,
+                                                                     double *__restrict__ part_d, int32_t *__restrict__ part_i) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q0 = ((int64_t)blockIdx.y * NN_WARPS + warp) * TQ;
+    if (q0 >= n_q) return;
+    const int64_t lo = (int64_t)blockIdx.x * slice_len;
+    int64_t hi = lo + slice_len;
+    if (hi > n_nodes) hi = n_nodes;
+    double qx[TQ], qy[TQ], bd[TQ];
+    int bi[TQ];
+#pragma unroll
+    for (int t = 0; t < TQ; t++) {
+        int64_t q = q0 + t < n_q ? q0 + t : n_q - 1;
+        qx[t] = (double)__ldg(qxy + 2 * q);
+        qy[t] = (double)__ldg(qxy + 2 * q + 1);
+        bd[t] = INFINITY;
+        bi[t] = 0x7fffffff;
+    }
+    // slice_len is even and x, y are 16-byte aligned (checked by the launcher): double2 loads
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    const double2 *y2 = reinterpret_cast<const double2 *>(y);
+    int64_t p = (lo >> 1) + lane, pend = hi >> 1; // pair index
+    for (; p < pend; p += 32) {
+        double2 xv = __ldg(x2 + p), yv = __ldg(y2 + p);
+        int i0 = (int)(p << 1);
+#pragma unroll
+        for (int t = 0; t < TQ; t++) {
+            double dx = qx[t] - xv.x, dy = qy[t] - yv.x;
+            double d = dx * dx + dy * dy;
+            if (d < bd[t]) { bd[t] = d; bi[t] = i0; }
+            dx = qx[t] - xv.y; dy = qy[t] - yv.y;
+            d = dx * dx + dy * dy;
+            if (d < bd[t]) { bd[t] = d; bi[t] = i0 + 1; }
+        }
+    }
+    if ((hi & 1) && lane == 0 && hi == n_nodes) { // odd tail node of the last slice
+        int i0 = (int)(hi - 1);
+        double xs = __ldg(x + i0), ys = __ldg(y + i0);
+#pragma unroll
+        for (int t = 0; t < TQ; t++) {
+            double dx = qx[t] - xs, dy = qy[t] - ys;
+            double d = dx * dx + dy * dy;
+            if (d < bd[t] || (d == bd[t] && i0 < bi[t])) { bd[t] = d; bi[t] = i0; }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TQ; t++) {
+        double d = bd[t];
+        int i = bi[t];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double od = __shfl_xor_sync(0xffffffffu, d, off);
+            int oi = __shfl_xor_sync(0xffffffffu, i, off);
+            if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+        }
+        if (lane == 0 && q0 + t < n_q) {
+            part_d[(int64_t)blockIdx.x * n_q + q0 + t] = d;
+            part_i[(int64_t)blockIdx.x * n_q + q0 + t] = i;
+        }
+    }
+}
+
+__global__ void nearest_final_kernel(const double *__restrict__ part_d, const int32_t *__restrict__ part_i, int n_slices, int64_t n_q,
+                                     int32_t *__restrict__ idx, double *__restrict__ d2) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n_q) return;
+    double bd = INFINITY;
+    int bi = 0x7fffffff;
+    for (int s = 0; s < n_slices; s++) {
+        double d = part_d[(int64_t)s * n_q + q];
+        int i = part_i[(int64_t)s * n_q + q];
+        if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
+    }
+    idx[q] = (bi == 0x7fffffff) ? -1 : bi;
+    if (d2) d2[q] = bd;
+}
+
+// ===========================================================================
+// K2 rrt_batch
+// ===========================================================================
+struct RrtDev {
+    const uint32_t *bits;
+    int H, W, wpr;
+    const int32_t *map_id;
+    BikeParams P;
+    int64_t nq;
+    int K;
+    const double *start, *goal;
+    const int32_t *sxy;
+    const double *sth;
+    double *nx, *ny, *nth;
+    int32_t *parent;
+    double *u;
+    int32_t *n_nodes, *sol, *status, *iters;
+    int32_t *it_near, *it_new;
+    uint8_t *it_code, *los_log;
+    int32_t *n_los;
+    unsigned long long *counters;
+    int32_t *tab; // [nq][tsize] open-addressing index table for the `in G.keys()` tests
+    int tsize;
+};
+
+__device__ __forceinline__ unsigned hash3(double x, double y, double t) {
+    // value-equality hash: -0.0 and +0.0 must collide (Python: -0.0 == 0.0)
+    unsigned long long a = (unsigned long long)__double_as_longlong(x + 0.0);
+    unsigned long long b = (unsigned long long)__double_as_longlong(y + 0.0);
+    unsigned long long c = (unsigned long long)__double_as_longlong(t + 0.0);
+    unsigned long long h = a * 0x9E3779B97F4A7C15ull;
+    h ^= (b + 0x7F4A7C159E3779B9ull + (h << 6) + (h >> 2));
+    h *= 0xC2B2AE3D27D4EB4Full;
+    h ^= (c + 0x165667B19E3779F9ull + (h << 6) + (h >> 2));
+    h ^= h >> 29;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 32;
+    return (unsigned)h;
+}
+
+// index of the tree node equal (by value) to (x, y, t), or -1   [rrt.py:151, :179]
+__device__ __forceinline__ int tree_find(const int32_t *tab, int tmask, const double *nx, const double *ny, const double *nth, double x,
+                                         double y, double t, unsigned long long &probes) {
+    unsigned s = hash3(x, y, t) & (unsigned)tmask;
+    for (;;) {
+        int e = tab[s];
+        probes++;
+        if (e == 0) return -1;
+        int i = e - 1;
+        if (nx[i] == x && ny[i] == y && nth[i] == t) return i;
+        s = (s + 1) & (unsigned)tmask;
+    }
+}
+__device__ __forceinline__ void tree_insert(int32_t *tab, int tmask, double x, double y, double t, int idx) {
+    unsigned s = hash3(x, y, t) & (unsigned)tmask;
+    while (tab[s] != 0) s = (s + 1) & (unsigned)tmask;
+    tab[s] = idx + 1;
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) rrt_kernel(const RrtDev a) {
+    const Group<G> g;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    if (q >= a.nq) return; // whole groups leave together
+    const int K = a.K;
+    const bool lead = g.gl == 0;
+    Grid m;
+    m.W = a.W; m.H = a.H; m.wpr = a.wpr;
+    m.bits = a.bits + (a.map_id ? (size_t)a.map_id[q] * a.H * a.wpr : 0);
+    const BikeParams &P = a.P;
+    double *nx = a.nx + q * K, *ny = a.ny + q * K, *nth = a.nth + q * K;
+    int32_t *parent = a.parent + q * K;
+    double *uo = a.u ? a.u + q * (int64_t)K * 5 : nullptr;
+    const int32_t *sxy = a.sxy + q * (int64_t)(K - 1) * 2;
+    const double *sth = a.sth + q * (int64_t)(K - 1);
+    int32_t *it_near = a.it_near ? a.it_near + q * (int64_t)(K - 1) : nullptr;
+    int32_t *it_new = a.it_new ? a.it_new + q * (int64_t)(K - 1) : nullptr;
+    uint8_t *it_code = a.it_code ? a.it_code + q * (int64_t)(K - 1) : nullptr;
+    uint8_t *los_log = a.los_log ? a.los_log + q * (int64_t)(K - 1) * 2 : nullptr;
+    int32_t *tab = a.tab + q * (int64_t)a.tsize;
+    const int tmask = a.tsize - 1;
+    unsigned long long c_scan = 0, c_los = 0, c_lospx = 0, c_arcpx = 0, c_arcang = 0, c_steer = 0, c_drive = 0, c_probe = 0;
+
+    for (int i = g.gl; i < a.tsize; i += G) tab[i] = 0;
+    const double gx = a.goal[3 * q], gy = a.goal[3 * q + 1], gth = standardangle(a.goal[3 * q + 2]);
+    if (lead) {
+        nx[0] = a.start[3 * q]; ny[0] = a.start[3 * q + 1]; nth[0] = standardangle(a.start[3 * q + 2]);
+        parent[0] = -1;
+        if (uo) for (int j = 0; j < 5; j++) uo[j] = NAN;
+    }
+    g.sync();
+    if (lead) tree_insert(tab, tmask, nx[0], ny[0], nth[0], 0);
+    g.sync();
+    int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND;
+    int k;
+    for (k = 1; k < K; k++) {
+        const int it = k - 1;
+        const int sx = __ldg(sxy + 2 * it), sy = __ldg(sxy + 2 * it + 1);
+        const double qx = (double)sx, qy = (double)sy;
+        const double qth = standardangle(__ldg(sth + it));
+        int code, near = -1, newi = -1;
+        do {
+            if (!m.freespace(sx, sy)) { code = TRRT_IT_QRAND_BLOCKED; break; }                       // rrt.py:148
+            if (tree_find(tab, tmask, nx, ny, nth, qx, qy, qth, c_probe) >= 0) { code = TRRT_IT_QRAND_IN_TREE; break; } // rrt.py:151
+            // ---- nearest node: argmin of fp64 squared distance, lowest index on ties (rrt.py:156-158)
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            {
+                int i = g.gl;
+                for (; i + 3 * G < n; i += 4 * G) {
+                    double x0 = nx[i], y0 = ny[i], x1 = nx[i + G], y1 = ny[i + G];
+                    double x2 = nx[i + 2 * G], y2 = ny[i + 2 * G], x3 = nx[i + 3 * G], y3 = ny[i + 3 * G];
+                    double dx, dy, d;
+                    dx = qx - x0; dy = qy - y0; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i; }
+                    dx = qx - x1; dy = qy - y1; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + G; }
+                    dx = qx - x2; dy = qy - y2; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 2 * G; }
+                    dx = qx - x3; dy = qy - y3; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 3 * G; }
+                }
+                for (; i < n; i += G) {
+                    double dx = qx - nx[i], dy = qy - ny[i];
+                    double d = dx * dx + dy * dy;
+                    if (d < bd) { bd = d; bi = i; }
+                }
+            }
+            g.min_di(bd, bi);
+            near = bi;
+            c_scan += (unsigned long long)n;
+            const double ox = nx[near], oy = ny[near], oth = nth[near];
+            // ---- steer (rrt.py:161)
+            Steer s;
+            steer(P, ox, oy, oth, qx, qy, qth, s);
+            c_steer++;
+            double wx = s.x, wy = s.y, wth = s.theta;
+            double us = standardangle(s.steer);
+            if (us < P.leftconstraint || us > P.rightconstraint) { code = TRRT_IT_STEER_CONSTRAINT; break; } // rrt.py:166
+            // ---- clearance (rrt.py:169): valid, bike_clear, front_of_bike_clear with short-circuit
+            bool ok = m.inb(trunc_ll(wx), trunc_ll(wy));
+            if (ok) {
+                double bx, by;
+                rotz(wth, P.bikelength, 0.0, bx, by);
+                ok = los_group<G>(g, m, trunc_ll(wx), trunc_ll(wy), trunc_ll(bx + wx), trunc_ll(by + wy), &c_lospx);
+                if (los_log && lead) los_log[nlos] = ok ? 1 : 0;
+                nlos++; c_los++;
+            }
+            if (ok) {
+                double bx, by;
+                rotz(wth, P.bikelength * P.frontclearance, 0.0, bx, by);
+                ok = los_group<G>(g, m, trunc_ll(wx), trunc_ll(wy), trunc_ll(bx + wx), trunc_ll(by + wy), &c_lospx);
+                if (los_log && lead) los_log[nlos] = ok ? 1 : 0;
+                nlos++; c_los++;
+            }
+            double udist = s.dist;
+            if (!ok) {
+                if (s.straight) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; code = TRRT_IT_NOT_RUN; break; } // rrt.py:170-171 -> TypeError
+                udist = s.dist / 3;
+                drive(P, ox, oy, oth, s.steer, s.iccx, s.iccy, s.rad, udist, wx, wy, wth);
+                c_drive++;
+            }
+            // ---- edge collision (rrt.py:173-176)
+            bool blocked;
+            if (s.straight) {
+                unsigned long long px = 0;
+                blocked = !los_group<G>(g, m, trunc_ll(ox), trunc_ll(oy), trunc_ll(wx), trunc_ll(wy), &px);
+                if (lead) c_arcpx += px;
+            } else blocked = arc_blocked<G>(g, m, ox, oy, wx, wy, s.steer, s.iccx, s.iccy, s.rad, &c_arcpx, &c_arcang);
+            if (blocked) { code = TRRT_IT_ARC_BLOCKED; break; }
+            // ---- insert (rrt.py:179-188)
+            int idx = tree_find(tab, tmask, nx, ny, nth, wx, wy, wth, c_probe);
+            if (idx < 0) {
+                if (n >= K) { status = TRRT_ERR_CAPACITY; code = TRRT_IT_NOT_RUN; break; }
+                idx = n++;
+                if (lead) {
+                    nx[idx] = wx; ny[idx] = wy; nth[idx] = wth;
+                    parent[idx] = -1;
+                    if (uo) for (int j = 0; j < 5; j++) uo[5 * idx + j] = NAN;
+                    tree_insert(tab, tmask, wx, wy, wth, idx);
+                }
+                code = TRRT_IT_NEW_NODE;
+            } else code = TRRT_IT_EXISTING_NODE;
+            newi = idx;
+            if (idx != near && lead) { // rrt.py:187-188
+                parent[idx] = near;
+                if (uo) { uo[5 * idx] = s.steer; uo[5 * idx + 1] = s.iccx; uo[5 * idx + 2] = s.iccy; uo[5 * idx + 3] = s.rad; uo[5 * idx + 4] = udist; }
+            }
+            g.sync(); // tree writes visible to the whole group before the next scan
+            // ---- goal test (rrt.py:191-201)
+            double dgx = gx - wx, dgy = gy - wy;
+            if (sqrt(dgx * dgx + dgy * dgy) < P.tol_xy && fabs(anglediff(wth, gth)) < P.tol_ang) { sol = idx; status = TRRT_OK_FOUND; }
+        } while (0);
+        if (lead) {
+            if (it_near) it_near[it] = near;
+            if (it_new) it_new[it] = newi;
+            if (it_code) it_code[it] = (uint8_t)code;
+        }
+        if (status == TRRT_OK_FOUND) { k++; break; }
+        if (status != TRRT_OK_NOT_FOUND) break;
+    }
+    const int iters = k - 1;
+    if (lead) {
+        for (int i = iters; i < K - 1; i++) {
+            if (it_near) it_near[i] = -1;
+            if (it_new) it_new[i] = -1;
+            if (it_code) it_code[i] = TRRT_IT_NOT_RUN;
+        }
+        a.n_nodes[q] = n;
+        a.sol[q] = sol;
+        a.status[q] = status;
+        a.iters[q] = iters;
+        if (a.n_los) a.n_los[q] = nlos;
+    }
+    if (a.counters) {
+        unsigned long long v[8] = {c_scan, c_los, c_lospx, c_arcpx, c_arcang, c_steer, c_drive, c_probe};
+        // scan / los / steer / drive / probe counts are group-uniform: take the leader's; arc counters are per lane
+        unsigned long long s3 = g.sum(c_arcpx), s4 = g.sum(c_arcang);
+        if (lead) {
+            v[3] = s3; v[4] = s4;
+            for (int j = 0; j < 8; j++) a.counters[q * 8 + j] = v[j];
+        }
+    }
+}
+
+// ===========================================================================
+// Single-step entry points: rrt.steer / rrt.drive / the rrt.py:173-174 edge
+// test for batches of independent inputs (one thread each).  They run exactly
+// the device functions the fused kernel uses.
+// ===========================================================================
+__global__ void steer_batch_kernel(BikeParams P, int64_t n, const double *__restrict__ in, double *__restrict__ out, uint8_t *__restrict__ straight) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Steer s;
+    steer(P, in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3], in[6 * i + 4], in[6 * i + 5], s);
+    double *o = out + 8 * i;
+    o[0] = s.x; o[1] = s.y; o[2] = s.theta; o[3] = s.steer; o[4] = s.iccx; o[5] = s.iccy; o[6] = s.rad; o[7] = s.dist;
+    straight[i] = s.straight ? 1 : 0;
+}
+__global__ void drive_batch_kernel(BikeParams P, int64_t n, const double *__restrict__ in, double *__restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *v = in + 8 * i;
+    double fx, fy, fa;
+    drive(P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], fx, fy, fa);
+    out[3 * i] = fx; out[3 * i + 1] = fy; out[3 * i + 2] = fa;
+}
+template <int G>
+__global__ void arc_batch_kernel(const uint32_t *__restrict__ bits, int H, int W, int wpr, const int32_t *__restrict__ map_id, int64_t n,
+                                 const double *__restrict__ in, uint8_t *__restrict__ blocked) {
+    const Group<G> g;
+    int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    if (i >= n) return;
+    Grid m;
+    m.W = W; m.H = H; m.wpr = wpr;
+    m.bits = bits + (map_id ? (size_t)map_id[i] * H * wpr : 0);
+    const double *v = in + 9 * i;
+    bool b;
+    if (v[8] != 0.0) b = !los_group<G>(g, m, trunc_ll(v[0]), trunc_ll(v[1]), trunc_ll(v[2]), trunc_ll(v[3]));
+    else b = arc_blocked<G>(g, m, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], nullptr, nullptr);
+    if (g.gl == 0) blocked[i] = b ? 1 : 0;
+}
+
+// ===========================================================================
+// rrt.findnearest (rrt.py:117-128): one block per query over the edge log.
+// The reference walks parents in tree order and children in append order with
+// a strict `<`, i.e. it returns the edge minimising (distance, parent index,
+// iteration) lexicographically.
+// ===========================================================================
+__global__ void __launch_bounds__(128) findnearest_kernel(BikeParams P, int64_t nq, int K, const double *__restrict__ nx, const double *__restrict__ ny,
+                                                          const double *__restrict__ nth, const int32_t *__restrict__ it_near,
+                                                          const int32_t *__restrict__ it_new, const double *__restrict__ goal, int32_t *best,
+                                                          double *best_dist) {
+    int64_t q = blockIdx.x;
+    const double gx = goal[3 * q], gy = goal[3 * q + 1], gth = goal[3 * q + 2];
+    double bd = INFINITY;
+    int bp = 0x7fffffff, bit = 0x7fffffff, bc = -1;
+    for (int it = threadIdx.x; it < K - 1; it += blockDim.x) {
+        int c = it_new[q * (int64_t)(K - 1) + it];
+        if (c < 0) continue;
+        int p = it_near[q * (int64_t)(K - 1) + it];
+        double dx = gx - nx[q * K + c], dy = gy - ny[q * K + c];
+        double d = P.weightxy * sqrt(dx * dx + dy * dy) + (1 - P.weightxy) * fabs(anglediff(nth[q * K + c], gth));
+        if (d < bd || (d == bd && (p < bp || (p == bp && it < bit)))) { bd = d; bp = p; bit = it; bc = c; }
+    }
+    __shared__ double sd[128];
+    __shared__ int sp[128], si[128], sc[128];
+    sd[threadIdx.x] = bd; sp[threadIdx.x] = bp; si[threadIdx.x] = bit; sc[threadIdx.x] = bc;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            int o = threadIdx.x + off;
+            if (sc[o] >= 0 && (sc[threadIdx.x] < 0 || sd[o] < sd[threadIdx.x] ||
+                               (sd[o] == sd[threadIdx.x] && (sp[o] < sp[threadIdx.x] || (sp[o] == sp[threadIdx.x] && si[o] < si[threadIdx.x]))))) {
+                sd[threadIdx.x] = sd[o]; sp[threadIdx.x] = sp[o]; si[threadIdx.x] = si[o]; sc[threadIdx.x] = sc[o];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { best[q] = sc[0]; best_dist[q] = sc[0] >= 0 ? sd[0] : NAN; }
+}
+
+// ===========================================================================
+// K3 theta_batch: A* / lazy Theta* (search.py:221-307), G >= 8 lanes per query.
+// Per-slot state in the workspace:
+//   cells[H*W]  {g fp64, parent int32, stamp uint32}; stamp = epoch<<2 | closed<<1 | open,
+//               an entry belongs to the running query only when its epoch matches
+//   heap[cap]   {f fp64, cell uint32}; cell index = x*W + y, so (f, cell) order is the
+//               reference's tuple order (f, (x, y))
+// Lane j < 8 owns neighbour j of the expanded node (order of search.py:187).
+// ===========================================================================
+struct __align__(16) Cell { double g; int parent; unsigned stamp; };
+struct __align__(16) HeapEnt { double f; unsigned c; unsigned pad; };
+
+struct ThetaDev {
+    const uint32_t *bits;
+    int H, W, wpr;
+    const int32_t *map_id;
+    int thetastar;
+    int64_t nq;
+    const int32_t *sg;
+    int32_t *path;
+    int path_cap;
+    int32_t *path_len;
+    double *cost;
+    int32_t *expanded, *status;
+    uint8_t *los_log;
+    int los_cap;
+    int32_t *n_los, *pushes;
+    int n_slots, heap_cap;
+    Cell *cells;
+    HeapEnt *heap;
+    unsigned long long *next_query; // dynamic query counter
+};
+
+__device__ __forceinline__ bool hless(double f1, unsigned c1, double f2, unsigned c2) { return f1 < f2 || (f1 == f2 && c1 < c2); }
+
+__device__ __forceinline__ bool heap_push(HeapEnt *h, int &size, int cap, double f, unsigned c) {
+    if (size >= cap) return false;
+    int i = size++;
+    while (i > 0) {
+        int p = (i - 1) >> 1;
+        HeapEnt e = h[p];
+        if (!hless(f, c, e.f, e.c)) break;
+        h[i] = e;
+        i = p;
+    }
+    HeapEnt n;
+    n.f = f; n.c = c; n.pad = 0;
+    h[i] = n;
+    return true;
+}
+__device__ __forceinline__ HeapEnt heap_pop(HeapEnt *h, int &size) {
+    HeapEnt top = h[0];
+    HeapEnt last = h[--size];
+    int i = 0;
+    for (;;) {
+        int c = 2 * i + 1;
+        if (c >= size) break;
+        HeapEnt a = h[c];
+        if (c + 1 < size) {
+            HeapEnt b = h[c + 1];
+            if (hless(b.f, b.c, a.f, a.c)) { a = b; c++; }
+        }
+        if (!hless(a.f, a.c, last.f, last.c)) break;
+        h[i] = a;
+        i = c;
+    }
+    if (size > 0) h[i] = last;
+    return top;
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
+    static_assert(G >= 8, "one lane per neighbour");
+    const Group<G> g;
+    const int slot = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G);
+    if (slot >= a.n_slots) return;
+    const bool lead = g.gl == 0;
+    const int W = a.W, H = a.H;
+    Cell *cells = a.cells + (size_t)slot * H * W;
+    HeapEnt *heap = a.heap + (size_t)slot * a.heap_cap;
+    // neighbour j = node - delta_j, delta in itertools.product([-1,0,1], repeat=2) minus (0,0)  (search.py:187-189)
+    const int j = g.gl & 7;
+    const int ndx = (j < 3) ? 1 : (j < 5 ? 0 : -1);
+    const int ndy = (j == 0 || j == 3 || j == 5) ? 1 : ((j == 1 || j == 6) ? 0 : -1);
+    const double ndist = (ndx != 0 && ndy != 0) ? sqrt(2.0) : 1.0; // L2norm of a unit step
+    unsigned epoch = 0;
+    for (;;) {
+        unsigned long long qq = 0;
+        if (lead) qq = atomicAdd(a.next_query, 1ull);
+        qq = g.bcast(qq, 0);
+        if (qq >= (unsigned long long)a.nq) break;
+        const int64_t q = (int64_t)qq;
+        epoch++;
+        Grid m;
+        m.W = W; m.H = H; m.wpr = a.wpr;
+        m.bits = a.bits + (a.map_id ? (size_t)a.map_id[q] * H * a.wpr : 0);
+        const int sx = a.sg[4 * q], sy = a.sg[4 * q + 1], gx = a.sg[4 * q + 2], gy = a.sg[4 * q + 3];
+        uint8_t *los_log = a.los_log ? a.los_log + q * (int64_t)a.los_cap : nullptr;
+        int status = TRRT_OK_NOT_FOUND, nlos = 0, npush = 0, nclosed = 0, hsize = 0;
+        bool overflow = false;
+        if (!m.inb(sx, sy) || !m.inb(gx, gy)) status = TRRT_ERR_ENDPOINT_INVALID;                  // search.py:222
+        else if (!m.free_nb(sx, sy) || !m.free_nb(gx, gy)) status = TRRT_ERR_ENDPOINT_BLOCKED;    // search.py:225
+        const unsigned goal_c = (unsigned)(gx * W + gy);
+        if (status == TRRT_OK_NOT_FOUND) {
+            const unsigned sc = (unsigned)(sx * W + sy);
+            // seed: expand the start node (search.py:237-244)
+            double pf = 0;
+            unsigned pc = 0;
+            bool has = false;
+            if (g.gl < 8) {
+                int x = sx + ndx, y = sy + ndy;
+                if (m.freespace(x, y)) {
+                    unsigned c = (unsigned)(x * W + y);
+                    Cell v; v.g = ndist; v.parent = (int)sc; v.stamp = (epoch << 2) | 1u;
+                    cells[c] = v;
+                    double hx = (double)(gx - x), hy = (double)(gy - y);
+                    pf = ndist + sqrt(hx * hx + hy * hy);
+                    pc = c; has = true;
+                }
+            }
+            if (lead) { Cell v; v.g = 0.0; v.parent = -1; v.stamp = (epoch << 2) | 2u; cells[sc] = v; }
+            nclosed = 1;
+            for (int t = 0; t < 8; t++) {
+                bool h1 = g.bcast(has, t); double f1 = g.bcast(pf, t); unsigned c1 = g.bcast(pc, t);
+                if (h1) { if (lead && !heap_push(heap, hsize, a.heap_cap, f1, c1)) overflow = true; npush++; }
+            }
+            hsize = g.bcast(hsize, 0);
+            overflow = g.bcast(overflow, 0);
+            g.sync();
+            // main loop (search.py:247-304)
+            while (hsize > 0 && !overflow) {
+                HeapEnt top;
+                if (lead) top = heap_pop(heap, hsize);
+                unsigned cur = g.bcast(top.c, 0);
+                hsize = g.bcast(hsize, 0);
+                Cell cc = cells[cur];
+                if (cc.stamp & 2u) continue; // already closed: stale heap copy (search.py:250-255); epoch matches by construction
+                const int cx = (int)(cur / (unsigned)W), cy = (int)(cur % (unsigned)W);
+                if (a.thetastar) { // search.py:258-263
+                    int px = cc.parent / W, py = cc.parent % W;
+                    bool los = los_group<G>(g, m, cx, cy, px, py);
+                    if (los_log && lead && nlos < a.los_cap) los_log[nlos] = los ? 1 : 0;
+                    nlos++;
+                    if (!los) {
+                        double v = INFINITY;
+                        int vi = 0x7fffffff;
+                        unsigned vc = 0;
+                        if (g.gl < 8) {
+                            int x = cx + ndx, y = cy + ndy;
+                            if (m.freespace(x, y)) {
+                                unsigned c = (unsigned)(x * W + y);
+                                Cell nb = cells[c];
+                                if ((nb.stamp >> 2) == epoch && (nb.stamp & 2u)) { v = nb.g + ndist; vi = j; vc = c; }
+                            }
+                        }
+                        double bv = v;
+                        int bj = vi;
+                        g.min_di(bv, bj);
+                        if (bj == 0x7fffffff) { status = TRRT_ERR_REF_RAISES_ARGMIN_EMPTY; break; }
+                        unsigned bc = g.bcast(vc, bj);
+                        cc.parent = (int)bc;
+                        cc.g = bv;
+                    }
+                }
+                cc.stamp = (epoch << 2) | 2u; // openSet.remove, closedSet.add (search.py:265-266)
+                if (lead) cells[cur] = cc;
+                nclosed++;
+                if (cur == goal_c) { status = TRRT_OK_FOUND; break; }
+                // neighbours (search.py:274-304), one lane each
+                const unsigned pcell = (unsigned)cc.parent;
+                const double gpar = a.thetastar ? cells[pcell].g : 0.0;
+                int np_ = 0;
+                double f1 = 0, f2 = 0;
+                unsigned nbc = 0;
+                if (g.gl < 8) {
+                    int x = cx + ndx, y = cy + ndy;
+                    if (m.freespace(x, y)) {
+                        unsigned c = (unsigned)(x * W + y);
+                        Cell nb = cells[c];
+                        bool mine = (nb.stamp >> 2) == epoch;
+                        bool closed = mine && (nb.stamp & 2u);
+                        if (!closed) {
+                            bool open = mine && (nb.stamp & 1u);
+                            double hx = (double)(gx - x), hy = (double)(gy - y);
+                            double hh = sqrt(hx * hx + hy * hy);
+                            double gn = cc.g + ndist;
+                            bool dirty = false;
+                            if (!open) { nb.g = gn; nb.parent = (int)cur; nb.stamp = (epoch << 2) | 1u; f1 = gn + hh; np_ = 1; dirty = true; }
+                            else if (gn < nb.g) { nb.g = gn; nb.parent = (int)cur; f1 = gn + hh; np_ = 1; dirty = true; }
+                            if (a.thetastar) {
+                                int ppx = (int)(pcell / (unsigned)W), ppy = (int)(pcell % (unsigned)W);
+                                double ex = (double)(x - ppx), ey = (double)(y - ppy);
+                                double g2 = gpar + sqrt(ex * ex + ey * ey);
+                                if (g2 < nb.g) {
+                                    nb.parent = (int)pcell; nb.g = g2; dirty = true;
+                                    if (np_ == 0) { f1 = g2 + hh; np_ = 1; } else { f2 = g2 + hh; np_ = 2; }
+                                }
+                            }
+                            if (dirty) cells[c] = nb;
+                            nbc = c;
+                        }
+                    }
+                }
+                for (int t = 0; t < 8; t++) {
+                    int cnt = g.bcast(np_, t);
+                    if (cnt == 0) continue;
+                    double fa = g.bcast(f1, t), fb = g.bcast(f2, t);
+                    unsigned c1 = g.bcast(nbc, t);
+                    if (lead) {
+                        if (!heap_push(heap, hsize, a.heap_cap, fa, c1)) overflow = true;
+                        if (cnt == 2 && !heap_push(heap, hsize, a.heap_cap, fb, c1)) overflow = true;
+                    }
+                    npush += cnt;
+                }
+                hsize = g.bcast(hsize, 0);
+                overflow = g.bcast(overflow, 0);
+                g.sync();
+            }
+            if (overflow) status = TRRT_ERR_CAPACITY;
+        }
+        g.sync();
+        // reconstruct (search.py:196-204) + cost, by the leader; the heap array is free now and serves as scratch
+        if (lead) {
+            int len = 0;
+            double cost = 0.0;
+            if (status == TRRT_OK_FOUND) {
+                unsigned c = goal_c;
+                unsigned *scratch = reinterpret_cast<unsigned *>(heap);
+                const long long scap = (long long)a.heap_cap * 4;
+                for (;;) {
+                    if (len < scap) scratch[len] = c;
+                    len++;
+                    int p = cells[c].parent;
+                    if (p < 0) break;
+                    c = (unsigned)p;
+                }
+                if (len > scap) status = TRRT_ERR_CAPACITY;
+                else {
+                    int32_t *path = a.path ? a.path + q * (int64_t)a.path_cap * 2 : nullptr;
+                    int ppx = 0, ppy = 0;
+                    for (int i = 0; i < len; i++) {
+                        unsigned cidx = scratch[len - 1 - i];
+                        int x = (int)(cidx / (unsigned)W), y = (int)(cidx % (unsigned)W);
+                        if (path && i < a.path_cap) { path[2 * i] = x; path[2 * i + 1] = y; }
+                        if (i > 0) { double ex = (double)(x - ppx), ey = (double)(y - ppy); cost += sqrt(ex * ex + ey * ey); }
+                        ppx = x; ppy = y;
+                    }
+                }
+            }
+            a.path_len[q] = len;
+            a.cost[q] = cost;
+            a.expanded[q] = (status == TRRT_OK_FOUND) ? nclosed : 0;
+            a.status[q] = status;
+            if (a.n_los) a.n_los[q] = nlos;
+            if (a.pushes) a.pushes[q] = npush;
+        }
+        g.sync();
+    }
+}
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int trrt_version(void) { return TRRT_VERSION; }
+
+const char *trrt_error_string(int err) {
+    switch (err) {
+    case TRRT_OK: return "ok";
+    case TRRT_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case TRRT_ERR_NONSQUARE_MAP: return "map must be square (reference bounds test, search.py:21)";
+    case TRRT_ERR_MAP_TOO_LARGE: return "map side exceeds 32768";
+    case TRRT_ERR_WORKSPACE_TOO_SMALL: return "workspace too small";
+    case TRRT_ERR_CUDA: return "CUDA error (see trrt_last_cuda_error)";
+    case TRRT_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown error";
+    }
+}
+const char *trrt_last_cuda_error(void) { return g_last_cuda_error; }
+
+void trrt_default_params(trrt_params *p) {
+    p->thetastar = 1; p->forwardonly = 1; p->bikelength = 5; p->leftconstraint = -65; p->rightconstraint = 65;
+    p->frontclearance = 2; p->maxdrivedist = 30; p->tol_xy = 10; p->tol_ang = 45; p->weightxy = .6;
+}
+
+size_t trrt_grid_words(int H, int W) { return (size_t)H * (size_t)((W + 31) / 32); }
+
+int trrt_pack_grid(const uint8_t *d_free, int n_maps, int H, int W, uint32_t *d_bits, void *stream) {
+    int e = check_map(n_maps, H, W);
+    if (e) return e;
+    if (!d_free || !d_bits) return TRRT_ERR_INVALID_ARGUMENT;
+    int wpr = (W + 31) / 32;
+    size_t total = (size_t)n_maps * H * wpr;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    pack_grid_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_free, n_maps, H, W, wpr, d_bits);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+int trrt_los_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32_t *d_map_id, const int32_t *d_seg, int64_t n,
+                   uint8_t *d_out, void *stream) {
+    int e = check_map(n_maps, H, W);
+    if (e) return e;
+    if (n < 0 || !d_bits || (n > 0 && (!d_seg || !d_out))) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TRRT_OK;
+    if (((uintptr_t)d_seg & 15) != 0) return TRRT_ERR_INVALID_ARGUMENT;
+    int64_t blocks = (n + 255) / 256;
+    los_batch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_bits, H, W, (W + 31) / 32, d_map_id, (const int4 *)d_seg, n, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+// slices are even-length so that every slice starts on a 16-byte boundary
+static void nearest_plan(int64_t n_nodes, int64_t n_q, int *tq, int *n_slices, int64_t *slice_len, int *n_qtiles) {
+    int t = n_q >= 512 ? 8 : (n_q >= 128 ? 4 : (n_q >= 16 ? 2 : 1));
+    int qtiles = (int)((n_q + (int64_t)NN_WARPS * t - 1) / ((int64_t)NN_WARPS * t));
+    // aim at ~8 CTAs per SM in total, at least 4096 nodes per slice
+    int64_t want = ((int64_t)sm_count() * 8 + qtiles - 1) / qtiles;
+    int64_t max_slices = (n_nodes + 4095) / 4096;
+    if (want > max_slices) want = max_slices;
+    if (want < 1) want = 1;
+    int64_t len = (n_nodes + want - 1) / want;
+    len = (len + 63) & ~(int64_t)63;
+    if (len < 64) len = 64;
+    int slices = (int)((n_nodes + len - 1) / len);
+    if (slices < 1) slices = 1;
+    *tq = t; *n_slices = slices; *slice_len = len; *n_qtiles = qtiles;
+}
+
+size_t trrt_nearest_workspace_bytes(int64_t n_nodes, int64_t n_q) {
+    if (n_nodes <= 0 || n_q <= 0) return 16;
+    int tq, ns, nt;
+    int64_t len;
+    nearest_plan(n_nodes, n_q, &tq, &ns, &len, &nt);
+    return (size_t)ns * (size_t)n_q * (sizeof(double) + sizeof(int32_t)) + 16;
+}
+
+int trrt_nearest_batch(const double *d_x, const double *d_y, int64_t n_nodes, const int32_t *d_qxy, int64_t n_q, int32_t *d_idx,
+                       double *d_d2, void *d_work, size_t work_bytes, void *stream) {
+    if (n_nodes < 0 || n_q < 0 || n_nodes > 0x7ffffffe) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n_q == 0) return TRRT_OK;
+    if (!d_qxy || !d_idx) return TRRT_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_nodes == 0) { // np.argmin([]) raises; report -1
+        CUDA_TRY(cudaMemsetAsync(d_idx, 0xff, (size_t)n_q * sizeof(int32_t), st));
+        return TRRT_OK;
+    }
+    if (!d_x || !d_y || !d_work) return TRRT_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)d_x & 15) || ((uintptr_t)d_y & 15) || ((uintptr_t)d_work & 7)) return TRRT_ERR_INVALID_ARGUMENT;
+    if (work_bytes < trrt_nearest_workspace_bytes(n_nodes, n_q)) return TRRT_ERR_WORKSPACE_TOO_SMALL;
+    int tq, ns, nt;
+    int64_t len;
+    nearest_plan(n_nodes, n_q, &tq, &ns, &len, &nt);
+    double *part_d = (double *)d_work;
+    int32_t *part_i = (int32_t *)(part_d + (size_t)ns * n_q);
+    dim3 grid((unsigned)ns, (unsigned)nt);
+    switch (tq) {
+    case 8: nearest_tile_kernel<8><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, len, part_d, part_i); break;
+    case 4: nearest_tile_kernel<4><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, len, part_d, part_i); break;
+    case 2: nearest_tile_kernel<2><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, len, part_d, part_i); break;
+    default: nearest_tile_kernel<1><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, len, part_d, part_i); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    nearest_final_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(part_d, part_i, ns, n_q, d_idx, d_d2);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+static int rrt_tsize(int K) {
+    int t = 16;
+    while (t < 2 * K) t <<= 1;
+    return t;
+}
+size_t trrt_rrt_workspace_bytes(int64_t n_queries, int32_t K) {
+    if (n_queries <= 0 || K <= 0) return 16;
+    return (size_t)n_queries * (size_t)rrt_tsize(K) * sizeof(int32_t) + 16;
+}
+
+static BikeParams to_dev(const trrt_params &p) {
+    BikeParams b;
+    b.thetastar = p.thetastar; b.forwardonly = p.forwardonly; b.bikelength = p.bikelength; b.leftconstraint = p.leftconstraint;
+    b.rightconstraint = p.rightconstraint; b.frontclearance = p.frontclearance; b.maxdrivedist = p.maxdrivedist;
+    b.tol_xy = p.tol_xy; b.tol_ang = p.tol_ang; b.weightxy = p.weightxy;
+    return b;
+}
+
+static int pick_lanes(int64_t nq, int requested, int min_g) {
+    if (requested != 0) return requested;
+    // enough warps to keep every SM sub-partition busy, as few lanes per query as that allows
+    int64_t target_warps = (int64_t)sm_count() * 16;
+    int64_t gsz = target_warps * 32 / (nq > 0 ? nq : 1);
+    int G = 32;
+    while (G > min_g && G > gsz) G >>= 1;
+    return G;
+}
+
+int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
+    if (!args) return TRRT_ERR_INVALID_ARGUMENT;
+    const trrt_rrt_args &A = *args;
+    int e = check_map(A.n_maps, A.H, A.W);
+    if (e) return e;
+    if (A.n_queries < 0 || A.K < 1) return TRRT_ERR_INVALID_ARGUMENT;
+    if (A.n_queries == 0) return TRRT_OK;
+    if (!A.d_bits || !A.d_start || !A.d_goal || (A.K > 1 && (!A.d_sample_xy || !A.d_sample_th)) || !A.d_node_x || !A.d_node_y || !A.d_node_th ||
+        !A.d_parent || !A.d_n_nodes || !A.d_sol || !A.d_status || !A.d_iters || !A.d_work)
+        return TRRT_ERR_INVALID_ARGUMENT;
+    if (A.d_los_log && !A.d_n_los) return TRRT_ERR_INVALID_ARGUMENT;
+    if (A.work_bytes < trrt_rrt_workspace_bytes(A.n_queries, A.K)) return TRRT_ERR_WORKSPACE_TOO_SMALL;
+    if ((uintptr_t)A.d_work & 3) return TRRT_ERR_INVALID_ARGUMENT;
+    int G = pick_lanes(A.n_queries, A.lanes_per_query, 1);
+    RrtDev d;
+    d.bits = A.d_bits; d.H = A.H; d.W = A.W; d.wpr = (A.W + 31) / 32; d.map_id = A.d_map_id; d.P = to_dev(A.params);
+    d.nq = A.n_queries; d.K = A.K; d.start = A.d_start; d.goal = A.d_goal; d.sxy = A.d_sample_xy; d.sth = A.d_sample_th;
+    d.nx = A.d_node_x; d.ny = A.d_node_y; d.nth = A.d_node_th; d.parent = A.d_parent; d.u = A.d_u;
+    d.n_nodes = A.d_n_nodes; d.sol = A.d_sol; d.status = A.d_status; d.iters = A.d_iters;
+    d.it_near = A.d_it_near; d.it_new = A.d_it_new; d.it_code = A.d_it_code; d.los_log = A.d_los_log; d.n_los = A.d_n_los;
+    d.counters = (unsigned long long *)A.d_counters;
+    d.tab = (int32_t *)A.d_work; d.tsize = rrt_tsize(A.K);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 128;
+    int64_t blocks = (A.n_queries * G + threads - 1) / threads;
+    switch (G) {
+    case 1: rrt_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    case 2: rrt_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    case 4: rrt_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    case 8: rrt_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    case 16: rrt_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    case 32: rrt_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    default: return TRRT_ERR_INVALID_ARGUMENT;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+int trrt_steer_batch(const trrt_params *params, int64_t n, const double *d_in, double *d_out, uint8_t *d_straight, void *stream) {
+    if (!params || n < 0) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TRRT_OK;
+    if (!d_in || !d_out || !d_straight) return TRRT_ERR_INVALID_ARGUMENT;
+    steer_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(to_dev(*params), n, d_in, d_out, d_straight);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+int trrt_drive_batch(const trrt_params *params, int64_t n, const double *d_in, double *d_out, void *stream) {
+    if (!params || n < 0) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TRRT_OK;
+    if (!d_in || !d_out) return TRRT_ERR_INVALID_ARGUMENT;
+    drive_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(to_dev(*params), n, d_in, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+int trrt_arc_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32_t *d_map_id, int64_t n, const double *d_in,
+                   uint8_t *d_blocked, int lanes, void *stream) {
+    int e = check_map(n_maps, H, W);
+    if (e) return e;
+    if (n < 0) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TRRT_OK;
+    if (!d_bits || !d_in || !d_blocked) return TRRT_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    int wpr = (W + 31) / 32;
+    if (lanes == 0) lanes = 8;
+    int64_t blocks = (n * lanes + 127) / 128;
+    switch (lanes) {
+    case 1: arc_batch_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(d_bits, H, W, wpr, d_map_id, n, d_in, d_blocked); break;
+    case 2: arc_batch_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(d_bits, H, W, wpr, d_map_id, n, d_in, d_blocked); break;
+    case 4: arc_batch_kernel<4><<<(unsigned)blocks, 128, 0, st>>>(d_bits, H, W, wpr, d_map_id, n, d_in, d_blocked); break;
+    case 8: arc_batch_kernel<8><<<(unsigned)blocks, 128, 0, st>>>(d_bits, H, W, wpr, d_map_id, n, d_in, d_blocked); break;
+    case 16: arc_batch_kernel<16><<<(unsigned)blocks, 128, 0, st>>>(d_bits, H, W, wpr, d_map_id, n, d_in, d_blocked); break;
+    case 32: arc_batch_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(d_bits, H, W, wpr, d_map_id, n, d_in, d_blocked); break;
+    default: return TRRT_ERR_INVALID_ARGUMENT;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+int trrt_findnearest_batch(const trrt_params *params, int64_t n_queries, int32_t K, const double *d_node_x, const double *d_node_y,
+                           const double *d_node_th, const int32_t *d_n_nodes, const int32_t *d_it_near, const int32_t *d_it_new,
+                           const double *d_goal, int32_t *d_best, double *d_best_dist, void *stream) {
+    (void)d_n_nodes;
+    if (!params || n_queries < 0 || K < 1) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n_queries == 0) return TRRT_OK;
+    if (!d_node_x || !d_node_y || !d_node_th || !d_it_near || !d_it_new || !d_goal || !d_best || !d_best_dist) return TRRT_ERR_INVALID_ARGUMENT;
+    findnearest_kernel<<<(unsigned)n_queries, 128, 0, (cudaStream_t)stream>>>(to_dev(*params), n_queries, K, d_node_x, d_node_y, d_node_th,
+                                                                                d_it_near, d_it_new, d_goal, d_best, d_best_dist);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+static void theta_plan(trrt_theta_args *A, int *G) {
+    int g = A->lanes_per_query;
+    if (g == 0) g = pick_lanes(A->n_queries, 0, 8);
+    if (g < 8) g = 8;
+    *G = g;
+    if (A->n_slots <= 0) {
+        int64_t resident = (int64_t)sm_count() * 16 * 32 / g; // 16 warps per SM
+        A->n_slots = (int32_t)(A->n_queries < resident ? (A->n_queries > 0 ? A->n_queries : 1) : resident);
+    }
+    if (A->heap_cap <= 0) {
+        int64_t c = 2ll * A->H * A->W;
+        if (c < 4096) c = 4096;
+        A->heap_cap = (int32_t)c;
+    }
+}
+static size_t theta_cells_bytes(const trrt_theta_args *A) { return (size_t)A->n_slots * A->H * A->W * sizeof(Cell); }
+static size_t theta_heap_bytes(const trrt_theta_args *A) { return (size_t)A->n_slots * A->heap_cap * sizeof(HeapEnt); }
+
+size_t trrt_theta_workspace_bytes(trrt_theta_args *args) {
+    if (!args) return 0;
+    int G;
+    theta_plan(args, &G);
+    return 256 + theta_cells_bytes(args) + theta_heap_bytes(args);
+}
+
+int trrt_theta_batch(const trrt_theta_args *args, void *stream) {
+    if (!args) return TRRT_ERR_INVALID_ARGUMENT;
+    trrt_theta_args A = *args;
+    int e = check_map(A.n_maps, A.H, A.W);
+    if (e) return e;
+    if (A.n_queries < 0) return TRRT_ERR_INVALID_ARGUMENT;
+    if (A.n_queries == 0) return TRRT_OK;
+    if (!A.d_bits || !A.d_start_goal || !A.d_path_len || !A.d_cost || !A.d_expanded || !A.d_status || !A.d_work) return TRRT_ERR_INVALID_ARGUMENT;
+    if (A.d_path && A.path_cap < 1) return TRRT_ERR_INVALID_ARGUMENT;
+    if (A.d_los_log && (A.los_cap < 1 || !A.d_n_los)) return TRRT_ERR_INVALID_ARGUMENT;
+    if ((uintptr_t)A.d_work & 15) return TRRT_ERR_INVALID_ARGUMENT;
+    int G;
+    theta_plan(&A, &G);
+    if (G != 8 && G != 16 && G != 32) return TRRT_ERR_INVALID_ARGUMENT;
+    size_t need = 256 + theta_cells_bytes(&A) + theta_heap_bytes(&A);
+    if (A.work_bytes < need) return TRRT_ERR_WORKSPACE_TOO_SMALL;
+    cudaStream_t st = (cudaStream_t)stream;
+    ThetaDev d;
+    d.bits = A.d_bits; d.H = A.H; d.W = A.W; d.wpr = (A.W + 31) / 32; d.map_id = A.d_map_id; d.thetastar = A.thetastar;
+    d.nq = A.n_queries; d.sg = A.d_start_goal; d.path = A.d_path; d.path_cap = A.path_cap; d.path_len = A.d_path_len; d.cost = A.d_cost;
+    d.expanded = A.d_expanded; d.status = A.d_status; d.los_log = A.d_los_log; d.los_cap = A.los_cap; d.n_los = A.d_n_los;
+    d.pushes = A.d_pushes; d.n_slots = A.n_slots; d.heap_cap = A.heap_cap;
+    char *w = (char *)A.d_work;
+    d.next_query = (unsigned long long *)w;
+    d.cells = (Cell *)(w + 256);
+    d.heap = (HeapEnt *)(w + 256 + theta_cells_bytes(&A));
+    // stamps must start at epoch 0 (= untouched) and the query counter at 0
+    CUDA_TRY(cudaMemsetAsync(w, 0, 256 + theta_cells_bytes(&A), st));
+    const int threads = 128;
+    int64_t blocks = ((int64_t)A.n_slots * G + threads - 1) / threads;
+    switch (G) {
+    case 8: theta_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    case 16: theta_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    default: theta_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+} // extern "C"

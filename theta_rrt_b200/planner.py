@@ -1,0 +1,306 @@
+"""Batched planner front-end over libthetarrt.so.
+
+Every method accepts either host data (numpy / sequences, copied to the GPU
+through pinned memory) or torch CUDA tensors (used in place) and returns torch
+tensors resident on the device; `.host()` on a result copies it back.  The
+calls only enqueue work on torch's current stream of the planner's device.
+There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from .grid import OccupancyGrid
+from .params import Params
+
+STATUS_NAMES = {0: "OK_FOUND", 1: "OK_NOT_FOUND", 2: "ERR_ENDPOINT_INVALID", 3: "ERR_ENDPOINT_BLOCKED",
+                4: "ERR_REF_RAISES_DRIVE_NONE", 5: "ERR_REF_RAISES_ARGMIN_EMPTY", 6: "ERR_CAPACITY"}
+IT_NEW_NODE, IT_EXISTING_NODE, IT_QRAND_BLOCKED, IT_QRAND_IN_TREE, IT_STEER_CONSTRAINT, IT_ARC_BLOCKED = range(6)
+IT_NOT_RUN = 255
+COUNTER_NAMES = ("nodes_scanned", "los_calls", "los_pixels", "arc_candidate_pixels", "arc_angle_tests",
+                 "steer_calls", "drive_calls", "hash_probes")
+
+
+def _host_dict(obj):
+    out = {}
+    for k, v in obj.__dict__.items():
+        out[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v
+    return out
+
+
+@dataclass
+class RrtResult:
+    K: int
+    node_x: torch.Tensor
+    node_y: torch.Tensor
+    node_theta: torch.Tensor
+    parent: torch.Tensor
+    n_nodes: torch.Tensor
+    sol: torch.Tensor
+    status: torch.Tensor
+    iters: torch.Tensor
+    u: torch.Tensor | None = None
+    it_near: torch.Tensor | None = None
+    it_new: torch.Tensor | None = None
+    it_code: torch.Tensor | None = None
+    los_log: torch.Tensor | None = None
+    n_los: torch.Tensor | None = None
+    counters: torch.Tensor | None = None
+    lanes: int = 0
+
+    def host(self):
+        return _host_dict(self)
+
+
+@dataclass
+class ThetaResult:
+    path: torch.Tensor
+    path_len: torch.Tensor
+    cost: torch.Tensor
+    expanded: torch.Tensor
+    status: torch.Tensor
+    los_log: torch.Tensor | None = None
+    n_los: torch.Tensor | None = None
+    pushes: torch.Tensor | None = None
+    extra: dict = field(default_factory=dict)
+
+    def host(self):
+        return _host_dict(self)
+
+
+class Planner:
+    """Device-resident planner for one OccupancyGrid (one or several same-size maps)."""
+
+    def __init__(self, grid: OccupancyGrid, params: Params | None = None):
+        if not torch.cuda.is_available():
+            raise _lib.TrrtError("no CUDA device: theta_rrt_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.grid = grid
+        self.device = grid.device
+        self.params = params or Params()
+        self._work = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _dev(self, a, dtype, shape=None):
+        """numpy/sequence -> device tensor through pinned memory; CUDA tensors pass through."""
+        if isinstance(a, torch.Tensor):
+            t = a
+            if t.device != self.device:
+                t = t.to(self.device, non_blocking=True)
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            t = t.contiguous()
+        else:
+            npdt = {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}[dtype]
+            h = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=npdt)))
+            t = h.pin_memory().to(self.device, non_blocking=True) if h.numel() else h.to(self.device)
+        if shape is not None:
+            t = t.reshape(shape)
+        return t
+
+    def _scratch(self, key, nbytes):
+        """Grow-only scratch buffers, one per kernel family (caller-owned workspace of the C ABI)."""
+        cur = self._work.get(key)
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+            self._work[key] = cur
+        return cur
+
+    def _map_ids(self, map_id, n):
+        if map_id is None:
+            return None
+        t = self._dev(map_id, torch.int32, (n,))
+        return t
+
+    # ------------------------------------------------------------------ K4
+    def los(self, seg, map_id=None, out=None):
+        """search.lineofsight for segments int32 [n,4] = (x0,y0,x1,y1).  Returns uint8 [n] (1 = visible)."""
+        with torch.cuda.device(self.device):
+            seg = self._dev(seg, torch.int32).reshape(-1, 4)
+            n = seg.shape[0]
+            mid = self._map_ids(map_id, n)
+            if out is None:
+                out = torch.empty(n, dtype=torch.uint8, device=self.device)
+            g = self.grid
+            _lib.check(self.lib.trrt_los_batch(g.bits.data_ptr(), g.n_maps, g.H, g.W,
+                                               mid.data_ptr() if mid is not None else None, seg.data_ptr(), n,
+                                               out.data_ptr(), self._stream()), "trrt_los_batch")
+        return out
+
+    # ------------------------------------------------------------------ K1
+    def nearest(self, x, y, qxy, want_d2=False):
+        """Nearest tree node (rrt.py:156-158) for integer query points int32 [q,2] over SoA x, y float64 [n]."""
+        with torch.cuda.device(self.device):
+            x = self._dev(x, torch.float64).reshape(-1)
+            y = self._dev(y, torch.float64).reshape(-1)
+            qxy = self._dev(qxy, torch.int32).reshape(-1, 2)
+            n, nq = x.shape[0], qxy.shape[0]
+            idx = torch.empty(nq, dtype=torch.int32, device=self.device)
+            d2 = torch.empty(nq, dtype=torch.float64, device=self.device) if want_d2 else None
+            wb = self.lib.trrt_nearest_workspace_bytes(n, nq)
+            work = self._scratch("nearest", wb)
+            _lib.check(self.lib.trrt_nearest_batch(x.data_ptr(), y.data_ptr(), n, qxy.data_ptr(), nq, idx.data_ptr(),
+                                                   d2.data_ptr() if want_d2 else None, work.data_ptr(), work.numel(),
+                                                   self._stream()), "trrt_nearest_batch")
+        return (idx, d2) if want_d2 else idx
+
+    # ------------------------------------------------------------------ K2
+    def rrt(self, starts, goals, sample_xy, sample_th, K=None, params=None, map_id=None, logs=False, want_u=True,
+            counters=False, lanes=0):
+        """rrt.rrt for a batch.  starts/goals float64 [q,3] (x, y, theta_deg); sample_xy int32 [q,K-1,2];
+        sample_th float64 [q,K-1].  K = builtins.K (node capacity; K-1 iterations)."""
+        P = params or self.params
+        with torch.cuda.device(self.device):
+            starts = self._dev(starts, torch.float64).reshape(-1, 3)
+            goals = self._dev(goals, torch.float64).reshape(-1, 3)
+            nq = starts.shape[0]
+            sample_th = self._dev(sample_th, torch.float64).reshape(nq, -1)
+            if K is None:
+                K = sample_th.shape[1] + 1
+            K = int(K)
+            if sample_th.shape[1] != K - 1:
+                raise ValueError(f"sample stream has {sample_th.shape[1]} iterations, K-1 = {K - 1}")
+            sample_xy = self._dev(sample_xy, torch.int32).reshape(nq, K - 1, 2)
+            mid = self._map_ids(map_id, nq)
+            dev = self.device
+            f64 = dict(dtype=torch.float64, device=dev)
+            i32 = dict(dtype=torch.int32, device=dev)
+            res = RrtResult(K=K, node_x=torch.empty((nq, K), **f64), node_y=torch.empty((nq, K), **f64),
+                            node_theta=torch.empty((nq, K), **f64), parent=torch.empty((nq, K), **i32),
+                            n_nodes=torch.empty(nq, **i32), sol=torch.empty(nq, **i32), status=torch.empty(nq, **i32),
+                            iters=torch.empty(nq, **i32))
+            if want_u:
+                res.u = torch.empty((nq, K, 5), **f64)
+            if logs:
+                res.it_near = torch.empty((nq, K - 1), **i32)
+                res.it_new = torch.empty((nq, K - 1), **i32)
+                res.it_code = torch.empty((nq, K - 1), dtype=torch.uint8, device=dev)
+                res.los_log = torch.zeros((nq, 2 * (K - 1)), dtype=torch.uint8, device=dev)
+                res.n_los = torch.empty(nq, **i32)
+            if counters:
+                res.counters = torch.zeros((nq, 8), dtype=torch.int64, device=dev)
+            wb = self.lib.trrt_rrt_workspace_bytes(nq, K)
+            work = self._scratch("rrt", wb)
+            g = self.grid
+            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            a = _lib.CRrtArgs(d_bits=g.bits.data_ptr(), n_maps=g.n_maps, H=g.H, W=g.W, d_map_id=ptr(mid),
+                              params=P.to_c(), n_queries=nq, K=K, lanes_per_query=int(lanes),
+                              d_start=starts.data_ptr(), d_goal=goals.data_ptr(), d_sample_xy=sample_xy.data_ptr(),
+                              d_sample_th=sample_th.data_ptr(), d_node_x=res.node_x.data_ptr(),
+                              d_node_y=res.node_y.data_ptr(), d_node_th=res.node_theta.data_ptr(),
+                              d_parent=res.parent.data_ptr(), d_u=ptr(res.u), d_n_nodes=res.n_nodes.data_ptr(),
+                              d_sol=res.sol.data_ptr(), d_status=res.status.data_ptr(), d_iters=res.iters.data_ptr(),
+                              d_it_near=ptr(res.it_near), d_it_new=ptr(res.it_new), d_it_code=ptr(res.it_code),
+                              d_los_log=ptr(res.los_log), d_n_los=ptr(res.n_los), d_counters=ptr(res.counters),
+                              d_work=work.data_ptr(), work_bytes=work.numel())
+            _lib.check(self.lib.trrt_rrt_batch(C.byref(a), self._stream()), "trrt_rrt_batch")
+            res.lanes = int(lanes)
+            # keep inputs alive until the stream has consumed them
+            res._keep = (starts, goals, sample_xy, sample_th, mid)
+        return res
+
+    def findnearest(self, res: RrtResult, goals, params=None):
+        """rrt.findnearest (rrt.py:117-128) for every query of an RrtResult produced with logs=True."""
+        if res.it_near is None:
+            raise ValueError("findnearest needs the edge log: run rrt(..., logs=True)")
+        P = params or self.params
+        with torch.cuda.device(self.device):
+            goals = self._dev(goals, torch.float64).reshape(-1, 3)
+            nq = goals.shape[0]
+            best = torch.empty(nq, dtype=torch.int32, device=self.device)
+            dist = torch.empty(nq, dtype=torch.float64, device=self.device)
+            cp = P.to_c()
+            _lib.check(self.lib.trrt_findnearest_batch(C.byref(cp), nq, res.K, res.node_x.data_ptr(),
+                                                       res.node_y.data_ptr(), res.node_theta.data_ptr(),
+                                                       res.n_nodes.data_ptr(), res.it_near.data_ptr(),
+                                                       res.it_new.data_ptr(), goals.data_ptr(), best.data_ptr(),
+                                                       dist.data_ptr(), self._stream()), "trrt_findnearest_batch")
+        return best, dist
+
+    # ------------------------------------------------------------------ single steps
+    def steer(self, inputs, params=None):
+        """rrt.steer for rows (ox, oy, theta, gx, gy, thetagoal).  Returns (out float64 [n,8], straight uint8 [n])."""
+        P = params or self.params
+        with torch.cuda.device(self.device):
+            inp = self._dev(inputs, torch.float64).reshape(-1, 6)
+            n = inp.shape[0]
+            out = torch.empty((n, 8), dtype=torch.float64, device=self.device)
+            straight = torch.empty(n, dtype=torch.uint8, device=self.device)
+            cp = P.to_c()
+            _lib.check(self.lib.trrt_steer_batch(C.byref(cp), n, inp.data_ptr(), out.data_ptr(), straight.data_ptr(),
+                                                 self._stream()), "trrt_steer_batch")
+        return out, straight
+
+    def drive(self, inputs, params=None):
+        """rrt.drive for rows (ox, oy, theta, u.steer, iccx, iccy, rad, dist).  Returns float64 [n,3]."""
+        P = params or self.params
+        with torch.cuda.device(self.device):
+            inp = self._dev(inputs, torch.float64).reshape(-1, 8)
+            n = inp.shape[0]
+            out = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+            cp = P.to_c()
+            _lib.check(self.lib.trrt_drive_batch(C.byref(cp), n, inp.data_ptr(), out.data_ptr(), self._stream()),
+                       "trrt_drive_batch")
+        return out
+
+    def arc_blocked(self, inputs, map_id=None, lanes=0):
+        """rrt.py:173-174 for rows (bx, by, lx, ly, u.steer, iccx, iccy, rad, straight).  Returns uint8 [n]."""
+        with torch.cuda.device(self.device):
+            inp = self._dev(inputs, torch.float64).reshape(-1, 9)
+            n = inp.shape[0]
+            mid = self._map_ids(map_id, n)
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+            g = self.grid
+            _lib.check(self.lib.trrt_arc_batch(g.bits.data_ptr(), g.n_maps, g.H, g.W,
+                                               mid.data_ptr() if mid is not None else None, n, inp.data_ptr(),
+                                               out.data_ptr(), int(lanes), self._stream()), "trrt_arc_batch")
+        return out
+
+    # ------------------------------------------------------------------ K3
+    def theta(self, start_goal, thetastar=None, map_id=None, path_cap=None, log_los=False, lanes=0, n_slots=0,
+              heap_cap=0):
+        """search.astar for queries int32 [q,4] = (sx, sy, gx, gy)."""
+        if thetastar is None:
+            thetastar = self.params.THETASTAR
+        with torch.cuda.device(self.device):
+            sg = self._dev(start_goal, torch.int32).reshape(-1, 4)
+            nq = sg.shape[0]
+            mid = self._map_ids(map_id, nq)
+            g = self.grid
+            if path_cap is None:
+                path_cap = 4 * (g.H + g.W)
+            dev = self.device
+            i32 = dict(dtype=torch.int32, device=dev)
+            res = ThetaResult(path=torch.full((nq, path_cap, 2), -1, **i32), path_len=torch.empty(nq, **i32),
+                              cost=torch.empty(nq, dtype=torch.float64, device=dev), expanded=torch.empty(nq, **i32),
+                              status=torch.empty(nq, **i32), n_los=torch.empty(nq, **i32),
+                              pushes=torch.empty(nq, **i32))
+            los_cap = 0
+            if log_los:
+                los_cap = g.H * g.W
+                res.los_log = torch.zeros((nq, los_cap), dtype=torch.uint8, device=dev)
+            ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+            a = _lib.CThetaArgs(d_bits=g.bits.data_ptr(), n_maps=g.n_maps, H=g.H, W=g.W, d_map_id=ptr(mid),
+                                thetastar=int(bool(thetastar)), lanes_per_query=int(lanes), n_queries=nq,
+                                d_start_goal=sg.data_ptr(), d_path=res.path.data_ptr(), path_cap=int(path_cap),
+                                d_path_len=res.path_len.data_ptr(), d_cost=res.cost.data_ptr(),
+                                d_expanded=res.expanded.data_ptr(), d_status=res.status.data_ptr(),
+                                d_los_log=ptr(res.los_log), los_cap=int(los_cap), d_n_los=res.n_los.data_ptr(),
+                                d_pushes=res.pushes.data_ptr(), n_slots=int(n_slots), heap_cap=int(heap_cap),
+                                d_work=None, work_bytes=0)
+            wb = self.lib.trrt_theta_workspace_bytes(C.byref(a))  # fills n_slots / heap_cap
+            work = self._scratch("theta", wb)
+            a.d_work = work.data_ptr()
+            a.work_bytes = work.numel()
+            _lib.check(self.lib.trrt_theta_batch(C.byref(a), self._stream()), "trrt_theta_batch")
+            res.extra = dict(n_slots=int(a.n_slots), heap_cap=int(a.heap_cap), workspace_bytes=int(wb))
+            res._keep = (sg, mid)
+        return res
