@@ -1,0 +1,47 @@
+"""world_size-2 gloo test of the query sharding + result gather used by the multi-GPU path."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from theta_rrt_b200 import shard
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 4096, 65536, 65537):
+        for w in (1, 2, 3, 4, 8):
+            r = [shard.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(s for s in shard.shard_sizes(n, w)) - min(s for s in shard.shard_sizes(n, w)) <= 1
+
+
+def _worker(rank, world, port, n):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard.shard_range(n, rank, world)
+    # per-query record = (query id, id squared, rank)
+    ids = torch.arange(lo, hi, dtype=torch.int64)
+    local = torch.stack([ids, ids * ids, torch.full_like(ids, rank)], dim=1)
+    full = shard.gather_records(local, n, dst=0)
+    if rank == 0:
+        assert full.shape == (n, 3)
+        assert torch.equal(full[:, 0], torch.arange(n)) and torch.equal(full[:, 1], torch.arange(n) ** 2)
+        assert full[:, 2].tolist() == [0] * (n // 2) + [1] * (n - n // 2)
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [9, 64])
+def test_gather_records_world2(n):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
