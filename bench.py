@@ -236,6 +236,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--queries", type=int, default=NQ_PER_GPU, help="queries per GPU (default: the cfg-3 size)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per query of the fused kernel (0 = auto)")
+    ap.add_argument("--schedule", type=int, default=0, help="0 = speculative window (default), 1 = cooperative")
     ap.add_argument("--skip-secondary", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
@@ -277,7 +278,7 @@ def main():
     torch.cuda.synchronize()
 
     # one untimed instrumented run: counters for the algorithmic-byte accounting
-    r0 = planner.rrt(*d_in, K=K, counters=True, lanes=args.lanes)
+    r0 = planner.rrt(*d_in, K=K, counters=True, lanes=args.lanes, schedule=args.schedule)
     torch.cuda.synchronize()
     counters = r0.counters.sum(dim=0).cpu().numpy().astype(np.int64)
     n_nodes_total = int(r0.n_nodes.sum().item())
@@ -292,7 +293,7 @@ def main():
     keep = {}
 
     def step_resident():
-        keep["res"] = planner.rrt(*d_in, K=K, lanes=args.lanes)
+        keep["res"] = planner.rrt(*d_in, K=K, lanes=args.lanes, schedule=args.schedule)
         launches["n"] += 1
         if dist_on:  # optional gather of the per-query summaries
             rec = torch.stack([keep["res"].n_nodes, keep["res"].sol, keep["res"].status], dim=1)
@@ -337,7 +338,7 @@ def main():
 
     def step_e2e():
         din = [t.to(dev, non_blocking=True) for t in h_in]
-        res = planner.rrt(*din, K=K, lanes=args.lanes)
+        res = planner.rrt(*din, K=K, lanes=args.lanes, schedule=args.schedule)
         for k, t in h_out.items():
             t.copy_(getattr(res, k), non_blocking=True)
         keep["e2e"] = (din, res)
@@ -358,7 +359,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg3: batched RRT, %d independent queries per GPU on map1.png (100x100), K=%d "
                                    "(5000 expansions each), tol_xy=0, seeded rand_conf streams" % (nq, K),
-                       "queries_per_gpu": nq, "K": K, "lanes_per_query": args.lanes or "auto",
+                       "queries_per_gpu": nq, "K": K, "lanes_per_query": args.lanes or 32,
+                       "schedule": "speculative window" if args.schedule == 0 else "cooperative",
                        "parallelism": "query-sharded x%d, no data-path collective" % world,
                        "l2_policy": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2" %
                                     ((h2d + d2h) / 1e9)},

@@ -201,16 +201,16 @@ def test_arc_blocked_vs_oracle(O, maps, lanes):
 
 
 # ------------------------------------------------------------------ fused RRT
-def run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, **params):
+def run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, schedule=0, **params):
     from oracle.c_oracle import Params as OP
     p = planner_for(free, **{k: v for k, v in params.items()})
-    res = p.rrt(starts, goals, sxy, sth, K=K, logs=True, counters=True, lanes=lanes).host()
+    res = p.rrt(starts, goals, sxy, sth, K=K, logs=True, counters=True, lanes=lanes, schedule=schedule).host()
     op = OP(**{k.lower(): v for k, v in params.items()})
     for q in range(len(starts)):
         o = O.rrt(free, ((starts[q, 0], starts[q, 1]), starts[q, 2]), ((goals[q, 0], goals[q, 1]), goals[q, 2]),
                   sxy[q], sth[q], op, K=K)
         n = o["n_nodes"]
-        tag = (q, lanes)
+        tag = (q, lanes, schedule)
         assert int(res["status"][q]) == o["status"], tag
         assert int(res["n_nodes"][q]) == n and int(res["sol"][q]) == o["sol"] and int(res["iters"][q]) == o["iters"], tag
         assert np.array_equal(res["it_code"][q], o["it_code"]), tag
@@ -225,14 +225,15 @@ def run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, **params):
     return res
 
 
+@pytest.mark.parametrize("schedule", [0, 1])
 @pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
-def test_rrt_cfg1_golden_and_oracle(O, maps, lanes):
+def test_rrt_cfg1_golden_and_oracle(O, maps, lanes, schedule):
     """BASELINE cfg 1: map1, ((5,5),0) -> ((90,50),90), seed-0 stream, K=300."""
     run = util.rrt_runs()[0]
     free = maps["map1"]
     K = int(run["K"][0])
     res = run_rrt_pair(O, free, run["start"][None], run["goal"][None], run["sxy"][None], run["sth"][None], K, lanes,
-                       tol_xy=float(run["tol_xy"][0]))
+                       schedule=schedule, tol_xy=float(run["tol_xy"][0]))
     n = int(res["n_nodes"][0])
     assert n == len(run["parent"]) and np.array_equal(res["parent"][0, :n], run["parent"])
     assert int(res["sol"][0]) == int(run["sol"][0]) and int(res["iters"][0]) == int(run["iterations"][0])
@@ -264,8 +265,9 @@ def test_rrt_all_goldens(O, maps):
         util.compare_rrt_with_reference(gpu, run, fa)
 
 
-@pytest.mark.parametrize("lanes,nq,K", [(32, 24, 1201), (8, 96, 801), (4, 64, 801), (1, 64, 401)])
-def test_rrt_batch_bitwise_vs_oracle(O, maps, lanes, nq, K):
+@pytest.mark.parametrize("schedule", [0, 1])
+@pytest.mark.parametrize("lanes,nq,K", [(32, 24, 1201), (16, 40, 1001), (8, 96, 801), (4, 64, 801), (1, 64, 401)])
+def test_rrt_batch_bitwise_vs_oracle(O, maps, lanes, nq, K, schedule):
     """cfg-3 style batch (random free start/goal, per-query seeded streams, tol_xy=0) -- bitwise vs oracle."""
     from theta_rrt_b200 import samples
     free = maps["map1"]
@@ -273,12 +275,15 @@ def test_rrt_batch_bitwise_vs_oracle(O, maps, lanes, nq, K):
     sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
     for q in range(nq):
         sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, q, free.shape)
-    res = run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, tol_xy=0.0)
-    # counters: scanned nodes = sum of tree sizes at each nearest call
+    res = run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, schedule=schedule, tol_xy=0.0)
+    # counters are defined on the sequential loop, so both schedules must report the same numbers
+    other = run_rrt_pair(O, free, starts[:8], goals[:8], sxy[:8], sth[:8], K, lanes, schedule=1 - schedule, tol_xy=0.0)
+    assert np.array_equal(res["counters"][:8, [0, 1, 2, 5, 6]], other["counters"][:, [0, 1, 2, 5, 6]])
     assert (res["counters"][:, 0] > 0).all()
 
 
-def test_rrt_full_size_one_query_k5001(O, maps):
+@pytest.mark.parametrize("lanes,schedule", [(32, 0), (16, 0), (16, 1)])
+def test_rrt_full_size_one_query_k5001(O, maps, lanes, schedule):
     """BASELINE cfg 3 size for a few queries: K=5001, bitwise vs oracle at full depth."""
     from theta_rrt_b200 import samples
     free = maps["map1"]
@@ -287,13 +292,29 @@ def test_rrt_full_size_one_query_k5001(O, maps):
     sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
     for q in range(nq):
         sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, q, free.shape)
-    run_rrt_pair(O, free, starts, goals, sxy, sth, K, 16, tol_xy=0.0)
+    run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, schedule=schedule, tol_xy=0.0)
 
 
-def test_rrt_goal_found_and_map2(O, maps):
+@pytest.mark.parametrize("lanes,schedule", [(32, 0), (8, 0), (8, 1)])
+def test_rrt_goal_found_and_map2(O, maps, lanes, schedule):
     run = util.rrt_runs()[2]
     run_rrt_pair(O, maps["map2"], run["start"][None], run["goal"][None], run["sxy"][None], run["sth"][None],
-                 int(run["K"][0]), 8, tol_xy=float(run["tol_xy"][0]))
+                 int(run["K"][0]), lanes, schedule=schedule, tol_xy=float(run["tol_xy"][0]))
+
+
+def test_rrt_large_radius_arcs_blank_map(O, maps):
+    """blank.png (300x300, no obstacles): long gentle arcs with radii far beyond the image exercise the deferred
+    (cooperative) raster of the speculative schedule and the out-of-image border logic."""
+    from theta_rrt_b200 import samples
+    free = maps["blank"].copy()
+    free[140:160, 40:260] = False  # one wall so that some arcs are blocked
+    nq, K = 12, 601
+    starts, goals = util.random_queries(free, nq, 77)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, 500 + q, free.shape)
+    for lanes, schedule in ((32, 0), (8, 0), (4, 1)):
+        run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, schedule=schedule, tol_xy=0.0)
 
 
 def test_findnearest_vs_oracle(O, maps):

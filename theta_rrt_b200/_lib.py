@@ -36,6 +36,7 @@ class CRrtArgs(C.Structure):
         ("d_bits", C.c_void_p), ("n_maps", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("d_map_id", C.c_void_p),
         ("params", CParams),
         ("n_queries", C.c_int64), ("K", C.c_int32), ("lanes_per_query", C.c_int32),
+        ("schedule", C.c_int32), ("reserved0", C.c_int32),
         ("d_start", C.c_void_p), ("d_goal", C.c_void_p), ("d_sample_xy", C.c_void_p), ("d_sample_th", C.c_void_p),
         ("d_node_x", C.c_void_p), ("d_node_y", C.c_void_p), ("d_node_th", C.c_void_p), ("d_parent", C.c_void_p),
         ("d_u", C.c_void_p), ("d_n_nodes", C.c_void_p), ("d_sol", C.c_void_p), ("d_status", C.c_void_p),

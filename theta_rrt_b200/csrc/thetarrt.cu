@@ -5,7 +5,8 @@
 //   los_batch_kernel      K4: search.lineofsight for independent segments
 //   nearest_tile_kernel   K1: fp64 argmin over SoA tree, query-tiled
 //   nearest_final_kernel      cross-slice reduction with lowest-index ties
-//   rrt_kernel<G>         K2: fused rrt.rrt loop, G lanes per query
+//   rrt_kernel_spec<G>    K2: fused rrt.rrt loop, speculative window of G iterations (trrt_rrt.cuh)
+//   rrt_kernel_coop<G>        same loop, G lanes cooperating on one iteration at a time
 //   findnearest_kernel    rrt.findnearest over the edge log
 //   theta_kernel<G>       K3: A* / lazy Theta*, G lanes per query
 //
@@ -20,6 +21,7 @@
 #include "../../include/thetarrt.h"
 #include "trrt_bike.cuh"
 #include "trrt_device.cuh"
+#include "trrt_rrt.cuh"
 
 using namespace trrt;
 
@@ -204,227 +206,6 @@ __global__ void nearest_final_kernel(const double *__restrict__ part_d, const in
     }
     idx[q] = (bi == 0x7fffffff) ? -1 : bi;
     if (d2) d2[q] = bd;
-}
-
-// ===========================================================================
-// K2 rrt_batch
-// ===========================================================================
-struct RrtDev {
-    const uint32_t *bits;
-    int H, W, wpr;
-    const int32_t *map_id;
-    BikeParams P;
-    int64_t nq;
-    int K;
-    const double *start, *goal;
-    const int32_t *sxy;
-    const double *sth;
-    double *nx, *ny, *nth;
-    int32_t *parent;
-    double *u;
-    int32_t *n_nodes, *sol, *status, *iters;
-    int32_t *it_near, *it_new;
-    uint8_t *it_code, *los_log;
-    int32_t *n_los;
-    unsigned long long *counters;
-    int32_t *tab; // [nq][tsize] open-addressing index table for the `in G.keys()` tests
-    int tsize;
-};
-
-__device__ __forceinline__ unsigned hash3(double x, double y, double t) {
-    // value-equality hash: -0.0 and +0.0 must collide (Python: -0.0 == 0.0)
-    unsigned long long a = (unsigned long long)__double_as_longlong(x + 0.0);
-    unsigned long long b = (unsigned long long)__double_as_longlong(y + 0.0);
-    unsigned long long c = (unsigned long long)__double_as_longlong(t + 0.0);
-    unsigned long long h = a * 0x9E3779B97F4A7C15ull;
-    h ^= (b + 0x7F4A7C159E3779B9ull + (h << 6) + (h >> 2));
-    h *= 0xC2B2AE3D27D4EB4Full;
-    h ^= (c + 0x165667B19E3779F9ull + (h << 6) + (h >> 2));
-    h ^= h >> 29;
-    h *= 0x94D049BB133111EBull;
-    h ^= h >> 32;
-    return (unsigned)h;
-}
-
-// index of the tree node equal (by value) to (x, y, t), or -1   [rrt.py:151, :179]
-__device__ __forceinline__ int tree_find(const int32_t *tab, int tmask, const double *nx, const double *ny, const double *nth, double x,
-                                         double y, double t, unsigned long long &probes) {
-    unsigned s = hash3(x, y, t) & (unsigned)tmask;
-    for (;;) {
-        int e = tab[s];
-        probes++;
-        if (e == 0) return -1;
-        int i = e - 1;
-        if (nx[i] == x && ny[i] == y && nth[i] == t) return i;
-        s = (s + 1) & (unsigned)tmask;
-    }
-}
-__device__ __forceinline__ void tree_insert(int32_t *tab, int tmask, double x, double y, double t, int idx) {
-    unsigned s = hash3(x, y, t) & (unsigned)tmask;
-    while (tab[s] != 0) s = (s + 1) & (unsigned)tmask;
-    tab[s] = idx + 1;
-}
-
-template <int G>
-__global__ void __launch_bounds__(128) rrt_kernel(const RrtDev a) {
-    const Group<G> g;
-    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
-    if (q >= a.nq) return; // whole groups leave together
-    const int K = a.K;
-    const bool lead = g.gl == 0;
-    Grid m;
-    m.W = a.W; m.H = a.H; m.wpr = a.wpr;
-    m.bits = a.bits + (a.map_id ? (size_t)a.map_id[q] * a.H * a.wpr : 0);
-    const BikeParams &P = a.P;
-    double *nx = a.nx + q * K, *ny = a.ny + q * K, *nth = a.nth + q * K;
-    int32_t *parent = a.parent + q * K;
-    double *uo = a.u ? a.u + q * (int64_t)K * 5 : nullptr;
-    const int32_t *sxy = a.sxy + q * (int64_t)(K - 1) * 2;
-    const double *sth = a.sth + q * (int64_t)(K - 1);
-    int32_t *it_near = a.it_near ? a.it_near + q * (int64_t)(K - 1) : nullptr;
-    int32_t *it_new = a.it_new ? a.it_new + q * (int64_t)(K - 1) : nullptr;
-    uint8_t *it_code = a.it_code ? a.it_code + q * (int64_t)(K - 1) : nullptr;
-    uint8_t *los_log = a.los_log ? a.los_log + q * (int64_t)(K - 1) * 2 : nullptr;
-    int32_t *tab = a.tab + q * (int64_t)a.tsize;
-    const int tmask = a.tsize - 1;
-    unsigned long long c_scan = 0, c_los = 0, c_lospx = 0, c_arcpx = 0, c_arcang = 0, c_steer = 0, c_drive = 0, c_probe = 0;
-
-    for (int i = g.gl; i < a.tsize; i += G) tab[i] = 0;
-    const double gx = a.goal[3 * q], gy = a.goal[3 * q + 1], gth = standardangle(a.goal[3 * q + 2]);
-    if (lead) {
-        nx[0] = a.start[3 * q]; ny[0] = a.start[3 * q + 1]; nth[0] = standardangle(a.start[3 * q + 2]);
-        parent[0] = -1;
-        if (uo) for (int j = 0; j < 5; j++) uo[j] = NAN;
-    }
-    g.sync();
-    if (lead) tree_insert(tab, tmask, nx[0], ny[0], nth[0], 0);
-    g.sync();
-    int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND;
-    int k;
-    for (k = 1; k < K; k++) {
-        const int it = k - 1;
-        const int sx = __ldg(sxy + 2 * it), sy = __ldg(sxy + 2 * it + 1);
-        const double qx = (double)sx, qy = (double)sy;
-        const double qth = standardangle(__ldg(sth + it));
-        int code, near = -1, newi = -1;
-        do {
-            if (!m.freespace(sx, sy)) { code = TRRT_IT_QRAND_BLOCKED; break; }                       // rrt.py:148
-            if (tree_find(tab, tmask, nx, ny, nth, qx, qy, qth, c_probe) >= 0) { code = TRRT_IT_QRAND_IN_TREE; break; } // rrt.py:151
-            // ---- nearest node: argmin of fp64 squared distance, lowest index on ties (rrt.py:156-158)
-            double bd = INFINITY;
-            int bi = 0x7fffffff;
-            {
-                int i = g.gl;
-                for (; i + 3 * G < n; i += 4 * G) {
-                    double x0 = nx[i], y0 = ny[i], x1 = nx[i + G], y1 = ny[i + G];
-                    double x2 = nx[i + 2 * G], y2 = ny[i + 2 * G], x3 = nx[i + 3 * G], y3 = ny[i + 3 * G];
-                    double dx, dy, d;
-                    dx = qx - x0; dy = qy - y0; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i; }
-                    dx = qx - x1; dy = qy - y1; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + G; }
-                    dx = qx - x2; dy = qy - y2; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 2 * G; }
-                    dx = qx - x3; dy = qy - y3; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 3 * G; }
-                }
-                for (; i < n; i += G) {
-                    double dx = qx - nx[i], dy = qy - ny[i];
-                    double d = dx * dx + dy * dy;
-                    if (d < bd) { bd = d; bi = i; }
-                }
-            }
-            g.min_di(bd, bi);
-            near = bi;
-            c_scan += (unsigned long long)n;
-            const double ox = nx[near], oy = ny[near], oth = nth[near];
-            // ---- steer (rrt.py:161)
-            Steer s;
-            steer(P, ox, oy, oth, qx, qy, qth, s);
-            c_steer++;
-            double wx = s.x, wy = s.y, wth = s.theta;
-            double us = standardangle(s.steer);
-            if (us < P.leftconstraint || us > P.rightconstraint) { code = TRRT_IT_STEER_CONSTRAINT; break; } // rrt.py:166
-            // ---- clearance (rrt.py:169): valid, bike_clear, front_of_bike_clear with short-circuit
-            bool ok = m.inb(trunc_ll(wx), trunc_ll(wy));
-            if (ok) {
-                double bx, by;
-                rotz(wth, P.bikelength, 0.0, bx, by);
-                ok = los_group<G>(g, m, trunc_ll(wx), trunc_ll(wy), trunc_ll(bx + wx), trunc_ll(by + wy), &c_lospx);
-                if (los_log && lead) los_log[nlos] = ok ? 1 : 0;
-                nlos++; c_los++;
-            }
-            if (ok) {
-                double bx, by;
-                rotz(wth, P.bikelength * P.frontclearance, 0.0, bx, by);
-                ok = los_group<G>(g, m, trunc_ll(wx), trunc_ll(wy), trunc_ll(bx + wx), trunc_ll(by + wy), &c_lospx);
-                if (los_log && lead) los_log[nlos] = ok ? 1 : 0;
-                nlos++; c_los++;
-            }
-            double udist = s.dist;
-            if (!ok) {
-                if (s.straight) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; code = TRRT_IT_NOT_RUN; break; } // rrt.py:170-171 -> TypeError
-                udist = s.dist / 3;
-                drive(P, ox, oy, oth, s.steer, s.iccx, s.iccy, s.rad, udist, wx, wy, wth);
-                c_drive++;
-            }
-            // ---- edge collision (rrt.py:173-176)
-            bool blocked;
-            if (s.straight) {
-                unsigned long long px = 0;
-                blocked = !los_group<G>(g, m, trunc_ll(ox), trunc_ll(oy), trunc_ll(wx), trunc_ll(wy), &px);
-                if (lead) c_arcpx += px;
-            } else blocked = arc_blocked<G>(g, m, ox, oy, wx, wy, s.steer, s.iccx, s.iccy, s.rad, &c_arcpx, &c_arcang);
-            if (blocked) { code = TRRT_IT_ARC_BLOCKED; break; }
-            // ---- insert (rrt.py:179-188)
-            int idx = tree_find(tab, tmask, nx, ny, nth, wx, wy, wth, c_probe);
-            if (idx < 0) {
-                if (n >= K) { status = TRRT_ERR_CAPACITY; code = TRRT_IT_NOT_RUN; break; }
-                idx = n++;
-                if (lead) {
-                    nx[idx] = wx; ny[idx] = wy; nth[idx] = wth;
-                    parent[idx] = -1;
-                    if (uo) for (int j = 0; j < 5; j++) uo[5 * idx + j] = NAN;
-                    tree_insert(tab, tmask, wx, wy, wth, idx);
-                }
-                code = TRRT_IT_NEW_NODE;
-            } else code = TRRT_IT_EXISTING_NODE;
-            newi = idx;
-            if (idx != near && lead) { // rrt.py:187-188
-                parent[idx] = near;
-                if (uo) { uo[5 * idx] = s.steer; uo[5 * idx + 1] = s.iccx; uo[5 * idx + 2] = s.iccy; uo[5 * idx + 3] = s.rad; uo[5 * idx + 4] = udist; }
-            }
-            g.sync(); // tree writes visible to the whole group before the next scan
-            // ---- goal test (rrt.py:191-201)
-            double dgx = gx - wx, dgy = gy - wy;
-            if (sqrt(dgx * dgx + dgy * dgy) < P.tol_xy && fabs(anglediff(wth, gth)) < P.tol_ang) { sol = idx; status = TRRT_OK_FOUND; }
-        } while (0);
-        if (lead) {
-            if (it_near) it_near[it] = near;
-            if (it_new) it_new[it] = newi;
-            if (it_code) it_code[it] = (uint8_t)code;
-        }
-        if (status == TRRT_OK_FOUND) { k++; break; }
-        if (status != TRRT_OK_NOT_FOUND) break;
-    }
-    const int iters = k - 1;
-    if (lead) {
-        for (int i = iters; i < K - 1; i++) {
-            if (it_near) it_near[i] = -1;
-            if (it_new) it_new[i] = -1;
-            if (it_code) it_code[i] = TRRT_IT_NOT_RUN;
-        }
-        a.n_nodes[q] = n;
-        a.sol[q] = sol;
-        a.status[q] = status;
-        a.iters[q] = iters;
-        if (a.n_los) a.n_los[q] = nlos;
-    }
-    if (a.counters) {
-        unsigned long long v[8] = {c_scan, c_los, c_lospx, c_arcpx, c_arcang, c_steer, c_drive, c_probe};
-        // scan / los / steer / drive / probe counts are group-uniform: take the leader's; arc counters are per lane
-        unsigned long long s3 = g.sum(c_arcpx), s4 = g.sum(c_arcang);
-        if (lead) {
-            v[3] = s3; v[4] = s4;
-            for (int j = 0; j < 8; j++) a.counters[q * 8 + j] = v[j];
-        }
-    }
 }
 
 // ===========================================================================
@@ -669,6 +450,7 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                     }
                 }
                 cc.stamp = (epoch << 2) | 2u; // openSet.remove, closedSet.add (search.py:265-266)
+                g.sync(); // every lane has read cells[cur] (lanes are not in lockstep) before the leader rewrites it
                 if (lead) cells[cur] = cc;
                 nclosed++;
                 if (cur == goal_c) { status = TRRT_OK_FOUND; break; }
@@ -915,7 +697,7 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
     if (A.d_los_log && !A.d_n_los) return TRRT_ERR_INVALID_ARGUMENT;
     if (A.work_bytes < trrt_rrt_workspace_bytes(A.n_queries, A.K)) return TRRT_ERR_WORKSPACE_TOO_SMALL;
     if ((uintptr_t)A.d_work & 3) return TRRT_ERR_INVALID_ARGUMENT;
-    int G = pick_lanes(A.n_queries, A.lanes_per_query, 1);
+    int G = A.lanes_per_query != 0 ? A.lanes_per_query : 32; // one warp per query unless told otherwise
     RrtDev d;
     d.bits = A.d_bits; d.H = A.H; d.W = A.W; d.wpr = (A.W + 31) / 32; d.map_id = A.d_map_id; d.P = to_dev(A.params);
     d.nq = A.n_queries; d.K = A.K; d.start = A.d_start; d.goal = A.d_goal; d.sxy = A.d_sample_xy; d.sth = A.d_sample_th;
@@ -927,15 +709,28 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 128;
     int64_t blocks = (A.n_queries * G + threads - 1) / threads;
-    switch (G) {
-    case 1: rrt_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(d); break;
-    case 2: rrt_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(d); break;
-    case 4: rrt_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(d); break;
-    case 8: rrt_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(d); break;
-    case 16: rrt_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(d); break;
-    case 32: rrt_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(d); break;
-    default: return TRRT_ERR_INVALID_ARGUMENT;
-    }
+    if (A.schedule == 1) { // cooperative: G lanes on one iteration at a time
+        switch (G) {
+        case 1: rrt_kernel_coop<1><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+        case 2: rrt_kernel_coop<2><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+        case 4: rrt_kernel_coop<4><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+        case 8: rrt_kernel_coop<8><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+        case 16: rrt_kernel_coop<16><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+        case 32: rrt_kernel_coop<32><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+        default: return TRRT_ERR_INVALID_ARGUMENT;
+        }
+    } else if (A.schedule == 0) { // speculative window of G iterations
+        const size_t smem = threads * sizeof(SpecRec);
+        switch (G) {
+        case 1: rrt_kernel_spec<1><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+        case 2: rrt_kernel_spec<2><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+        case 4: rrt_kernel_spec<4><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+        case 8: rrt_kernel_spec<8><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+        case 16: rrt_kernel_spec<16><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+        case 32: rrt_kernel_spec<32><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+        default: return TRRT_ERR_INVALID_ARGUMENT;
+        }
+    } else return TRRT_ERR_INVALID_ARGUMENT;
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }

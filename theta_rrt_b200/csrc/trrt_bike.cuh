@@ -34,7 +34,7 @@ __device__ __forceinline__ void quat_z(double deg, double &z, double &w) {
 }
 
 // Rotation.from_euler('z',deg,degrees=True).apply([vx,vy,0])[:2]
-__device__ __forceinline__ void rotz(double deg, double vx, double vy, double &ox, double &oy) {
+__device__ __noinline__ void rotz(double deg, double vx, double vy, double &ox, double &oy) {
     double z, w;
     quat_z(deg, z, w);
     double z2 = z * z, w2 = w * w, zw = z * w;
@@ -46,14 +46,14 @@ __device__ __forceinline__ void rotz(double deg, double vx, double vy, double &o
 }
 
 // rrt.py:73-77 (np.dot contracts: fma(v1y, v2y, v1x*v2x))
-__device__ __forceinline__ double anglebetween(double v1x, double v1y, double v2x, double v2y) {
+__device__ __noinline__ double anglebetween(double v1x, double v1y, double v2x, double v2y) {
     double dot = fma(v1y, v2y, v1x * v2x);
     double det = v2x * v1y - v1x * v2y;
     return standardangle(tl_atan2(det, dot) * (180.0 / TRRT_PI));
 }
 
 // rrt.py:108-115 given the two quaternions (so callers can reuse them)
-__device__ __forceinline__ double anglediff_q(double s1, double c1, double s2, double c2) {
+__device__ __noinline__ double anglediff_q(double s1, double c1, double s2, double c2) {
     double ns1 = -s1;
     double qz = c1 * s2 + c2 * ns1;
     double qw = c1 * c2 - ns1 * s2;
@@ -73,7 +73,7 @@ __device__ __forceinline__ double anglediff(double a1, double a2) {
     return anglediff_q(s1, c1, s2, c2);
 }
 
-__device__ __forceinline__ double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); } // np.linalg.norm
+__device__ __noinline__ double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); } // np.linalg.norm
 
 // rrt.py:42-46
 __device__ __forceinline__ void linefrompoints(double px, double py, double qx, double qy, double &a, double &b, double &c) {
@@ -92,7 +92,7 @@ __device__ __forceinline__ double arclength_to_angle(double radius, double arcle
 }
 
 // np.linalg.solve, 2x2 (dgesv: partial pivoting, reciprocal-pivot scaling). false = LinAlgError
-__device__ __forceinline__ bool solve2(double a1, double b1, double a2, double b2, double c1, double c2, double &x1, double &x2) {
+__device__ __noinline__ bool solve2(double a1, double b1, double a2, double b2, double c1, double c2, double &x1, double &x2) {
     if (fabs(a2) > fabs(a1)) {
         double t;
         t = a1; a1 = a2; a2 = t;
@@ -109,7 +109,7 @@ __device__ __forceinline__ bool solve2(double a1, double b1, double a2, double b
     return true;
 }
 // np.linalg.cond (2-norm) of [[a,b],[c,d]]
-__device__ __forceinline__ double cond2(double a, double b, double c, double d) {
+__device__ __noinline__ double cond2(double a, double b, double c, double d) {
     double E = a * a + b * b + c * c + d * d;
     double D = fabs(a * d - b * c);
     double disc = E * E - 4 * D * D;
@@ -274,7 +274,7 @@ __device__ __forceinline__ long long py_round(double v) { return (long long)rint
 // (DESIGN.md has the derivation; tests compare against the literal loop for
 // every r <= 2000).  Pixels outside the image are dropped (search.py:103).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ long long circle_x(long long r, long long t) {
+__device__ __noinline__ long long circle_x(long long r, long long t) {
     // largest x >= 0 with x*(x-1) < c, c = r*r - t*t > 0
     long long c = r * r - t * t;
     long long x = (long long)((1.0 + sqrt(1.0 + 4.0 * (double)c)) * 0.5);
@@ -282,7 +282,7 @@ __device__ __forceinline__ long long circle_x(long long r, long long t) {
     while ((x + 1) * x < c) ++x;
     return x;
 }
-__device__ __forceinline__ long long circle_tmax(long long r) {
+__device__ __noinline__ long long circle_tmax(long long r) {
     // largest t >= 0 with 2*t*t + t < r*r; -1 when r == 0
     if (r <= 0) return -1;
     long long rr = r * r;
@@ -292,7 +292,7 @@ __device__ __forceinline__ long long circle_tmax(long long r) {
     return t;
 }
 // is offset (a, b) from the centre one of the raster pixels?
-__device__ __forceinline__ bool circle_member(long long r, long long a, long long b) {
+__device__ __noinline__ bool circle_member(long long r, long long a, long long b) {
     long long p = a < 0 ? -a : a, q = b < 0 ? -b : b;
     if (p < q) { long long t = p; p = q; q = t; }
     if (p == q) return false; // never emitted (search.py:100 / loop condition)
@@ -330,47 +330,74 @@ __device__ __noinline__ bool arc_keeps_pixel(ArcTest &A, double bx, double by, d
     return (fob >= 0) || (bog >= 0);
 }
 
-// rrt.py:173-174 for a curved edge: is any pixel of getArc(begin, land, u) not free?
-// Candidate circle pixels are enumerated lane-parallel; only blocked in-bounds
-// pixels pay for the angular test (free pixels cannot change the answer).
-template <int G>
-__device__ __forceinline__ bool arc_blocked(const Group<G> &g, const Grid &m, double bx, double by, double lx, double ly,
-                                            double usteer, double iccx, double iccy, double rad,
-                                            unsigned long long *cand_px, unsigned long long *angle_tests) {
+// number of candidate pixels arc_blocked() would enumerate for this circle (rows in range x 2 mirrors)
+__device__ __noinline__ long long arc_candidates(const Grid &m, double iccx, double iccy, double rad) {
     long long xc = trunc_ll(iccx), yc = trunc_ll(iccy), r = trunc_ll(rad);
-    ArcTest A;
-    A.iccx = iccx; A.iccy = iccy; A.usteer = usteer; A.ready = false;
-    bool hit = false;
     long long tmax = circle_tmax(r);
-    // Row ranges t for which a reflection can fall inside the image:
-    //   kind 0: (xc +- x_t, yc + t)   kind 1: (xc +- x_t, yc - t)
-    //   kind 2: (xc + t, yc +- x_t)   kind 3: (xc - t, yc +- x_t)
     long long lo[4], hi[4];
-    lo[0] = -yc;             hi[0] = (long long)m.W - 1 - yc; // valid(): y < shape[1]
+    lo[0] = -yc;             hi[0] = (long long)m.W - 1 - yc;
     lo[1] = yc - (m.W - 1);  hi[1] = yc;
-    lo[2] = -xc;             hi[2] = (long long)m.H - 1 - xc; // valid(): x < shape[0]
+    lo[2] = -xc;             hi[2] = (long long)m.H - 1 - xc;
     lo[3] = xc - (m.H - 1);  hi[3] = xc;
+    long long total = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         long long a = lo[k] < 0 ? 0 : lo[k], b = hi[k] > tmax ? tmax : hi[k];
+        if (b >= a) total += (b - a + 1) * 2;
+    }
+    return total;
+}
+
+// rrt.py:173-174 for a curved edge: is any pixel of getArc(begin, land, u) not free?
+// Candidate circle pixels are enumerated lane-parallel; only blocked in-bounds
+// pixels pay for the angular test (free pixels cannot change the answer).
+// T = int when the radius fits 15 bits (almost always), long long otherwise.
+template <int G, typename T>
+__device__ __noinline__ bool arc_blocked_impl(const Group<G> &g, const Grid &m, double bx, double by, double lx, double ly, double usteer,
+                                              double iccx, double iccy, long long xc_, long long yc_, long long r_,
+                                              unsigned long long *cand_px, unsigned long long *angle_tests) {
+    const T r = (T)r_;
+    // centres far outside the image cannot reach it with a small radius; clamp so that T never overflows
+    const long long lim = (long long)1 << 20;
+    const T xc = (T)(sizeof(T) == 4 ? (xc_ > lim ? lim : (xc_ < -lim ? -lim : xc_)) : xc_);
+    const T yc = (T)(sizeof(T) == 4 ? (yc_ > lim ? lim : (yc_ < -lim ? -lim : yc_)) : yc_);
+    ArcTest A;
+    A.iccx = iccx; A.iccy = iccy; A.usteer = usteer; A.ready = false;
+    bool hit = false;
+    const T tmax = (T)circle_tmax(r_);
+    const T rr = r * r;
+    // Row ranges t for which a reflection can fall inside the image:
+    //   kind 0: (xc +- x_t, yc + t)   kind 1: (xc +- x_t, yc - t)
+    //   kind 2: (xc + t, yc +- x_t)   kind 3: (xc - t, yc +- x_t)
+    T lo[4], hi[4];
+    lo[0] = -yc;                 hi[0] = (T)m.W - 1 - yc; // valid(): y < shape[1]
+    lo[1] = yc - ((T)m.W - 1);   hi[1] = yc;
+    lo[2] = -xc;                 hi[2] = (T)m.H - 1 - xc; // valid(): x < shape[0]
+    lo[3] = xc - ((T)m.H - 1);   hi[3] = xc;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        T a = lo[k] < 0 ? 0 : lo[k], b = hi[k] > tmax ? tmax : hi[k];
         if (b < a) continue;
-        long long count = (b - a + 1) * 2; // two mirror pixels per row
+        T count = (b - a + 1) * 2; // two mirror pixels per row
         if (cand_px && g.gl == 0) *cand_px += (unsigned long long)count;
-        for (long long base = 0; base < count; base += G) {
-            long long j = base + g.gl;
+        T xt = -1; // x of the previous row handled by this lane (rows only grow, x only shrinks)
+        for (T base = 0; base < count; base += G) {
+            T j = base + g.gl;
             bool bad = false;
             if (j < count) {
-                long long t = a + (j >> 1);
-                long long xt = circle_x(r, t);
-                long long sgn = (j & 1) ? -1 : 1;
-                long long px, py;
-                if (k == 0) { px = xc + sgn * xt; py = yc + t; }
-                else if (k == 1) { px = xc + sgn * xt; py = yc - t; }
-                else if (k == 2) { px = xc + t; py = yc + sgn * xt; }
-                else { px = xc - t; py = yc + sgn * xt; }
-                if (m.inb(px, py) && !m.free_nb((int)px, (int)py)) {
+                T t = a + (j >> 1);
+                T c = rr - t * t;
+                if (xt < 0) xt = (t == 0) ? r : (T)circle_x(r_, (long long)t); // x_0 = r
+                while (xt * (xt - 1) >= c) --xt;
+                T sx = (j & 1) ? -xt : xt;
+                T px, py;
+                if (k == 0) { px = xc + sx; py = yc + t; }
+                else if (k == 1) { px = xc + sx; py = yc - t; }
+                else if (k == 2) { px = xc + t; py = yc + sx; }
+                else { px = xc - t; py = yc + sx; }
+                if (px >= 0 && py >= 0 && px < (T)m.H && py < (T)m.W && !m.free_nb((int)px, (int)py)) {
                     if (angle_tests) *angle_tests += 1;
-                    bad = arc_keeps_pixel(A, bx, by, lx, ly, px, py);
+                    bad = arc_keeps_pixel(A, bx, by, lx, ly, (long long)px, (long long)py);
                 }
             }
             if (g.any(bad)) { hit = true; break; }
@@ -380,42 +407,41 @@ __device__ __forceinline__ bool arc_blocked(const Group<G> &g, const Grid &m, do
     if (hit) return true;
     // diagonal-gap pixels (search.py:124-138): added when none of the 4-neighbours of
     // (xc+rnd, yc+rnd) is an emitted (in-bounds) raster pixel
-    long long rnd = py_round((double)r * 0.5 * sqrt(2.0));
-    long long tx = rnd, ty = rnd; // offsets of the test pixel
+    long long rnd = py_round((double)r_ * 0.5 * sqrt(2.0));
     bool drawmore = true;
     {
         const int nx[4] = {1, -1, 0, 0}, ny[4] = {0, 0, 1, -1};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            long long a = tx + nx[i], b = ty + ny[i];
-            if (m.inb(xc + a, yc + b) && circle_member(r, a, b)) drawmore = false;
+            long long a = rnd + nx[i], b = rnd + ny[i];
+            if (m.inb(xc_ + a, yc_ + b) && circle_member(r_, a, b)) drawmore = false;
         }
     }
     if (drawmore) {
         bool bad = false;
-        if (g.gl < 4) {
-            long long px = xc + ((g.gl == 0 || g.gl == 2) ? rnd : -rnd);
-            long long py = yc + ((g.gl == 0 || g.gl == 3) ? rnd : -rnd);
+        for (int i = g.gl; i < 4; i += G) { // (+,+) (-,-) (+,-) (-,+)
+            long long px = xc_ + ((i == 0 || i == 2) ? rnd : -rnd);
+            long long py = yc_ + ((i == 0 || i == 3) ? rnd : -rnd);
             if (m.inb(px, py) && !m.free_nb((int)px, (int)py)) {
                 if (angle_tests) *angle_tests += 1;
-                bad = arc_keeps_pixel(A, bx, by, lx, ly, px, py);
-            }
-        }
-        if (G < 4) { // fewer than 4 lanes: lane 0 walks the remaining diagonal pixels
-            for (int i = G; i < 4; i++) {
-                if (g.gl == 0) {
-                    long long px = xc + ((i == 0 || i == 2) ? rnd : -rnd);
-                    long long py = yc + ((i == 0 || i == 3) ? rnd : -rnd);
-                    if (m.inb(px, py) && !m.free_nb((int)px, (int)py)) {
-                        if (angle_tests) *angle_tests += 1;
-                        bad = bad || arc_keeps_pixel(A, bx, by, lx, ly, px, py);
-                    }
-                }
+                bad = bad || arc_keeps_pixel(A, bx, by, lx, ly, px, py);
             }
         }
         if (g.any(bad)) return true;
     }
     return false;
+}
+
+// One raster instantiation per use: a lane alone (G == 1, speculative phase) runs the 32-bit version and
+// must not be given radii >= 32768 (callers hand those to the group); groups run the 64-bit version.
+template <int G>
+__device__ __forceinline__ bool arc_blocked(const Group<G> &g, const Grid &m, double bx, double by, double lx, double ly,
+                                            double usteer, double iccx, double iccy, double rad,
+                                            unsigned long long *cand_px, unsigned long long *angle_tests) {
+    long long xc = trunc_ll(iccx), yc = trunc_ll(iccy), r = trunc_ll(rad);
+    if (G == 1 && r < 32768)
+        return arc_blocked_impl<G, int>(g, m, bx, by, lx, ly, usteer, iccx, iccy, xc, yc, r, cand_px, angle_tests);
+    return arc_blocked_impl<G, long long>(g, m, bx, by, lx, ly, usteer, iccx, iccy, xc, yc, r, cand_px, angle_tests);
 }
 
 } // namespace trrt

@@ -30,8 +30,13 @@
 
 #if defined(__CUDACC__)
 #define TL_FN __host__ __device__ __forceinline__
+/* the two entry points are real functions on the device: one copy each keeps the kernels' code
+   footprint inside the instruction cache (inlining them at ~40 call sites made a 380 KB kernel
+   that stalled 93% of the time on instruction fetch) */
+#define TL_ENTRY static __host__ __device__ __noinline__
 #else
 #define TL_FN static inline
+#define TL_ENTRY static inline
 #endif
 
 #define TL_PI 3.141592653589793116       /* np.pi */
@@ -102,7 +107,7 @@ TL_FN int tl_rem_pio2(double x, double *y0, double *y1) {
     return (int)((long long)fn & 3);
 }
 
-TL_FN void tl_sincos(double x, double *s, double *c) {
+TL_ENTRY void tl_sincos(double x, double *s, double *c) {
     double ax = fabs(x);
     if (!(ax < 1.0e300)) { /* inf / nan / absurd */
         *s = x - x; *c = x - x; return;
@@ -141,7 +146,7 @@ TL_FN double tl_atan_poly(double t) {
 }
 
 /* atan2 for finite, non-NaN arguments and the IEEE special cases numpy/libm define */
-TL_FN double tl_atan2(double y, double x) {
+TL_ENTRY double tl_atan2(double y, double x) {
     if (x != x || y != y) return x + y;
     double ay = fabs(y), ax = fabs(x);
     int yneg = signbit(y) ? 1 : 0, xneg = signbit(x) ? 1 : 0;

@@ -1,0 +1,486 @@
+// trrt_rrt.cuh -- K2: the fused rrt.rrt loop (rrt.py:130-206), G lanes per query.
+//
+// Two schedules produce bit-identical results:
+//
+//  * cooperative (schedule 1): the G lanes of a group work on ONE loop iteration at a time: the
+//    nearest scan, the Bresenham rays and the circle raster are lane-parallel, the scalar steer /
+//    drive math is computed redundantly by every lane.
+//
+//  * speculative window (schedule 0, default): the sample stream does not depend on the tree
+//    (rrt.py:144 draws before any test), and everything an iteration does after picking its
+//    nearest node depends only on (nearest node, sample, map).  So lane j of a group expands
+//    iteration k0+j against a SNAPSHOT of the tree (n0 nodes at the window start): its own fp64
+//    nearest scan (node loads are warp-uniform broadcasts, so the tree is read once per G
+//    iterations), steer, clearance rays, re-drive and edge raster.  The window is then committed
+//    in iteration order: `qrand in G` and `qnew in G` are answered by the hash index (which
+//    includes nodes inserted earlier in the window), and the snapshot nearest is corrected against
+//    the <= G nodes inserted earlier in the window (new nodes have higher indices, so the snapshot
+//    winner keeps ties).  Only when one of those nodes is strictly nearer (about 3% of iterations
+//    at G = 32 on map1) is the iteration recomputed, cooperatively, from the corrected node.
+//    The committed sequence is exactly the sequential loop.
+#pragma once
+#include "trrt_bike.cuh"
+
+namespace trrt {
+
+struct RrtDev {
+    const uint32_t *bits;
+    int H, W, wpr;
+    const int32_t *map_id;
+    BikeParams P;
+    int64_t nq;
+    int K;
+    const double *start, *goal;
+    const int32_t *sxy;
+    const double *sth;
+    double *nx, *ny, *nth;
+    int32_t *parent;
+    double *u;
+    int32_t *n_nodes, *sol, *status, *iters;
+    int32_t *it_near, *it_new;
+    uint8_t *it_code, *los_log;
+    int32_t *n_los;
+    unsigned long long *counters;
+    int32_t *tab; // [nq][tsize] open-addressing index table for the `in G.keys()` tests
+    int tsize;
+};
+
+__device__ __forceinline__ unsigned hash3(double x, double y, double t) {
+    // value-equality hash: -0.0 and +0.0 must collide (Python: -0.0 == 0.0)
+    unsigned long long a = (unsigned long long)__double_as_longlong(x + 0.0);
+    unsigned long long b = (unsigned long long)__double_as_longlong(y + 0.0);
+    unsigned long long c = (unsigned long long)__double_as_longlong(t + 0.0);
+    unsigned long long h = a * 0x9E3779B97F4A7C15ull;
+    h ^= (b + 0x7F4A7C159E3779B9ull + (h << 6) + (h >> 2));
+    h *= 0xC2B2AE3D27D4EB4Full;
+    h ^= (c + 0x165667B19E3779F9ull + (h << 6) + (h >> 2));
+    h ^= h >> 29;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 32;
+    return (unsigned)h;
+}
+
+// index of the tree node equal (by value) to (x, y, t), or -1   [rrt.py:151, :179]
+__device__ __forceinline__ int tree_find(const int32_t *tab, int tmask, const double *nx, const double *ny, const double *nth, double x,
+                                         double y, double t, unsigned long long &probes) {
+    unsigned s = hash3(x, y, t) & (unsigned)tmask;
+    for (;;) {
+        int e = tab[s];
+        probes++;
+        if (e == 0) return -1;
+        int i = e - 1;
+        if (nx[i] == x && ny[i] == y && nth[i] == t) return i;
+        s = (s + 1) & (unsigned)tmask;
+    }
+}
+__device__ __forceinline__ void tree_insert(int32_t *tab, int tmask, double x, double y, double t, int idx) {
+    unsigned s = hash3(x, y, t) & (unsigned)tmask;
+    while (tab[s] != 0) s = (s + 1) & (unsigned)tmask;
+    tab[s] = idx + 1;
+}
+
+// Outcome of one iteration from "nearest node chosen" to "edge tested" (rrt.py:161-176).
+enum { EX_ACCEPT = 100 }; // edge is free: proceed to insert (rrt.py:179)
+struct Expand {
+    double wx, wy, wth;                  // qnew (after the optional 1/3 re-drive)
+    double usteer, iccx, iccy, rad, udist; // u as stored in cameFrom
+    int code;                            // TRRT_IT_STEER_CONSTRAINT / TRRT_IT_ARC_BLOCKED / EX_ACCEPT
+    int flags;                           // bit0 straight, bit1 reference raises (Q7), bit2 goal reached,
+                                         // bits 4-5 number of LOS calls, bit 6/7 their results, bit 8 arc deferred
+    int lospx, arcpx, arcang;            // counters of this iteration
+    int drive;
+};
+
+// Everything after the nearest node is known.  ARC: group used for rays / raster (Group<1> = one lane alone).
+// defer_big_arcs: leave a curved edge with many candidate pixels untested (flag bit 8) for a cooperative pass.
+template <int GA>
+__device__ __noinline__ void expand_from(const Group<GA> &ga, const Grid &m, const BikeParams &P, double ox, double oy, double oth,
+                                            double qx, double qy, double qth, double gx, double gy, double gth, bool defer_big_arcs,
+                                            Expand &e) {
+    Steer s;
+    steer(P, ox, oy, oth, qx, qy, qth, s);
+    e.wx = s.x; e.wy = s.y; e.wth = s.theta;
+    e.usteer = s.steer; e.iccx = s.iccx; e.iccy = s.iccy; e.rad = s.rad; e.udist = s.dist;
+    e.flags = s.straight ? 1 : 0;
+    e.lospx = e.arcpx = e.arcang = e.drive = 0;
+    double us = standardangle(s.steer);
+    if (us < P.leftconstraint || us > P.rightconstraint) { e.code = TRRT_IT_STEER_CONSTRAINT; return; } // rrt.py:166
+    // clearance (rrt.py:169): valid, bike_clear, front_of_bike_clear with short-circuit
+    unsigned long long px = 0;
+    int nlos = 0;
+    bool ok = m.inb(trunc_ll(e.wx), trunc_ll(e.wy));
+    if (ok) {
+        double bx, by;
+        rotz(e.wth, P.bikelength, 0.0, bx, by);
+        ok = los_group<GA>(ga, m, trunc_ll(e.wx), trunc_ll(e.wy), trunc_ll(bx + e.wx), trunc_ll(by + e.wy), &px);
+        if (ok) e.flags |= 1 << 6;
+        nlos = 1;
+    }
+    if (ok) {
+        double bx, by;
+        rotz(e.wth, P.bikelength * P.frontclearance, 0.0, bx, by);
+        ok = los_group<GA>(ga, m, trunc_ll(e.wx), trunc_ll(e.wy), trunc_ll(bx + e.wx), trunc_ll(by + e.wy), &px);
+        if (ok) e.flags |= 1 << 7;
+        nlos = 2;
+    }
+    e.flags |= nlos << 4;
+    e.lospx = (int)px;
+    if (!ok) {
+        if (s.straight) { e.flags |= 2; e.code = TRRT_IT_NOT_RUN; return; } // rrt.py:170-171 -> TypeError in the reference
+        e.udist = s.dist / 3;
+        drive(P, ox, oy, oth, s.steer, s.iccx, s.iccy, s.rad, e.udist, e.wx, e.wy, e.wth);
+        e.drive = 1;
+    }
+    // goal test input (rrt.py:191-198) depends only on qnew
+    {
+        double dgx = gx - e.wx, dgy = gy - e.wy;
+        if (sqrt(dgx * dgx + dgy * dgy) < P.tol_xy && fabs(anglediff(e.wth, gth)) < P.tol_ang) e.flags |= 4;
+    }
+    // edge collision (rrt.py:173-176)
+    bool blocked;
+    if (s.straight) {
+        unsigned long long apx = 0;
+        blocked = !los_group<GA>(ga, m, trunc_ll(ox), trunc_ll(oy), trunc_ll(e.wx), trunc_ll(e.wy), &apx);
+        e.arcpx = (int)apx;
+    } else {
+        if (defer_big_arcs && (s.rad >= 32768.0 || arc_candidates(m, s.iccx, s.iccy, s.rad) > 64)) { e.flags |= 1 << 8; e.code = EX_ACCEPT; return; }
+        unsigned long long apx = 0, aang = 0;
+        blocked = arc_blocked<GA>(ga, m, ox, oy, e.wx, e.wy, s.steer, s.iccx, s.iccy, s.rad, &apx, &aang);
+        if (GA > 1) { apx = ga.sum(apx); aang = ga.sum(aang); }
+        e.arcpx = (int)apx; e.arcang = (int)aang;
+    }
+    e.code = blocked ? TRRT_IT_ARC_BLOCKED : EX_ACCEPT;
+}
+
+// fp64 nearest scan over nodes [0, n), G lanes cooperating (strided); result in every lane  (rrt.py:156-158)
+template <int G>
+__device__ __forceinline__ int nearest_coop(const Group<G> &g, const double *nx, const double *ny, int n, double qx, double qy) {
+    double bd = INFINITY;
+    int bi = 0x7fffffff;
+    int i = g.gl;
+    for (; i + 3 * G < n; i += 4 * G) {
+        double x0 = nx[i], y0 = ny[i], x1 = nx[i + G], y1 = ny[i + G];
+        double x2 = nx[i + 2 * G], y2 = ny[i + 2 * G], x3 = nx[i + 3 * G], y3 = ny[i + 3 * G];
+        double dx, dy, d;
+        dx = qx - x0; dy = qy - y0; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i; }
+        dx = qx - x1; dy = qy - y1; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + G; }
+        dx = qx - x2; dy = qy - y2; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 2 * G; }
+        dx = qx - x3; dy = qy - y3; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 3 * G; }
+    }
+    for (; i < n; i += G) {
+        double dx = qx - nx[i], dy = qy - ny[i];
+        double d = dx * dx + dy * dy;
+        if (d < bd) { bd = d; bi = i; }
+    }
+    g.min_di(bd, bi);
+    return bi;
+}
+
+struct RrtQuery {
+    Grid m;
+    double *nx, *ny, *nth;
+    int32_t *parent;
+    double *uo;
+    const int32_t *sxy;
+    const double *sth;
+    int32_t *it_near, *it_new;
+    uint8_t *it_code, *los_log;
+    int32_t *tab;
+    int tmask;
+    double gx, gy, gth;
+};
+
+template <int G>
+__device__ __forceinline__ void rrt_setup(const RrtDev &a, int64_t q, const Group<G> &g, RrtQuery &Q) {
+    const int K = a.K;
+    Q.m.W = a.W; Q.m.H = a.H; Q.m.wpr = a.wpr;
+    Q.m.bits = a.bits + (a.map_id ? (size_t)a.map_id[q] * a.H * a.wpr : 0);
+    Q.nx = a.nx + q * K; Q.ny = a.ny + q * K; Q.nth = a.nth + q * K;
+    Q.parent = a.parent + q * K;
+    Q.uo = a.u ? a.u + q * (int64_t)K * 5 : nullptr;
+    Q.sxy = a.sxy + q * (int64_t)(K - 1) * 2;
+    Q.sth = a.sth + q * (int64_t)(K - 1);
+    Q.it_near = a.it_near ? a.it_near + q * (int64_t)(K - 1) : nullptr;
+    Q.it_new = a.it_new ? a.it_new + q * (int64_t)(K - 1) : nullptr;
+    Q.it_code = a.it_code ? a.it_code + q * (int64_t)(K - 1) : nullptr;
+    Q.los_log = a.los_log ? a.los_log + q * (int64_t)(K - 1) * 2 : nullptr;
+    Q.tab = a.tab + q * (int64_t)a.tsize;
+    Q.tmask = a.tsize - 1;
+    for (int i = g.gl; i < a.tsize; i += G) Q.tab[i] = 0;
+    Q.gx = a.goal[3 * q]; Q.gy = a.goal[3 * q + 1]; Q.gth = standardangle(a.goal[3 * q + 2]);
+    if (g.gl == 0) {
+        Q.nx[0] = a.start[3 * q]; Q.ny[0] = a.start[3 * q + 1]; Q.nth[0] = standardangle(a.start[3 * q + 2]);
+        Q.parent[0] = -1;
+        if (Q.uo) for (int j = 0; j < 5; j++) Q.uo[j] = NAN;
+    }
+    g.sync();
+    if (g.gl == 0) tree_insert(Q.tab, Q.tmask, Q.nx[0], Q.ny[0], Q.nth[0], 0);
+    g.sync();
+}
+
+// rrt.py:179-201 for an accepted edge.  Uniform across the group; the leader writes.  Returns the node index.
+template <int G>
+__device__ __forceinline__ int rrt_insert(const Group<G> &g, const RrtQuery &Q, const Expand &e, int near, int K, int &n, int &code,
+                                          int &status, unsigned long long &probes, bool &inserted) {
+    inserted = false;
+    int idx = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes);
+    // Lanes of a group are NOT in lockstep (independent thread scheduling): every lane must have finished
+    // reading the tree and its index before the leader modifies them, or a late lane finds the node the
+    // leader has just inserted and the group's copies of `n` drift apart.
+    g.sync();
+    if (idx < 0) {
+        if (n >= K) { status = TRRT_ERR_CAPACITY; code = TRRT_IT_NOT_RUN; return -1; }
+        idx = n++;
+        inserted = true;
+        if (g.gl == 0) {
+            Q.nx[idx] = e.wx; Q.ny[idx] = e.wy; Q.nth[idx] = e.wth;
+            Q.parent[idx] = -1;
+            if (Q.uo) for (int j = 0; j < 5; j++) Q.uo[5 * idx + j] = NAN;
+            tree_insert(Q.tab, Q.tmask, e.wx, e.wy, e.wth, idx);
+        }
+        code = TRRT_IT_NEW_NODE;
+    } else code = TRRT_IT_EXISTING_NODE;
+    if (idx != near && g.gl == 0) { // rrt.py:187-188
+        Q.parent[idx] = near;
+        if (Q.uo) {
+            Q.uo[5 * idx] = e.usteer; Q.uo[5 * idx + 1] = (e.flags & 1) ? NAN : e.iccx; Q.uo[5 * idx + 2] = (e.flags & 1) ? NAN : e.iccy;
+            Q.uo[5 * idx + 3] = (e.flags & 1) ? NAN : e.rad; Q.uo[5 * idx + 4] = e.udist;
+        }
+    }
+    g.sync(); // tree + index writes visible to the whole group
+    return idx;
+}
+
+struct RrtCounters {
+    unsigned long long scan, los, lospx, arcpx, arcang, steer, drive, probe;
+};
+
+template <int G>
+__device__ __forceinline__ void rrt_finish(const RrtDev &a, int64_t q, const Group<G> &g, const RrtQuery &Q, int K, int iters, int n, int sol,
+                                           int status, int nlos, const RrtCounters &c) {
+    if (g.gl == 0) {
+        for (int i = iters; i < K - 1; i++) {
+            if (Q.it_near) Q.it_near[i] = -1;
+            if (Q.it_new) Q.it_new[i] = -1;
+            if (Q.it_code) Q.it_code[i] = TRRT_IT_NOT_RUN;
+        }
+        a.n_nodes[q] = n;
+        a.sol[q] = sol;
+        a.status[q] = status;
+        a.iters[q] = iters;
+        if (a.n_los) a.n_los[q] = nlos;
+        if (a.counters) {
+            unsigned long long *o = a.counters + q * 8;
+            o[0] = c.scan; o[1] = c.los; o[2] = c.lospx; o[3] = c.arcpx; o[4] = c.arcang; o[5] = c.steer; o[6] = c.drive; o[7] = c.probe;
+        }
+    }
+}
+
+// Applies the outcome `e` of iteration `it` (nearest node `near`) to the tree; uniform across the group.
+// Returns false when the loop must stop (goal reached or the reference would raise).
+template <int G>
+__device__ __forceinline__ bool rrt_commit(const Group<G> &g, const RrtQuery &Q, const Expand &e, int near, int K, int &n, int &nlos, int &sol,
+                                           int &status, int &code, int &newi, RrtCounters &c, bool &inserted) {
+    inserted = false;
+    c.steer++;
+    if (e.code == TRRT_IT_STEER_CONSTRAINT) { code = TRRT_IT_STEER_CONSTRAINT; return true; }
+    const int nl = (e.flags >> 4) & 3;
+    if (Q.los_log && g.gl == 0) {
+        if (nl >= 1) Q.los_log[nlos] = (e.flags >> 6) & 1;
+        if (nl >= 2) Q.los_log[nlos + 1] = (e.flags >> 7) & 1;
+    }
+    nlos += nl;
+    c.los += nl; c.lospx += e.lospx; c.arcpx += e.arcpx; c.arcang += e.arcang; c.drive += e.drive;
+    if (e.flags & 2) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; code = TRRT_IT_NOT_RUN; return false; }
+    if (e.code == TRRT_IT_ARC_BLOCKED) { code = TRRT_IT_ARC_BLOCKED; return true; }
+    newi = rrt_insert<G>(g, Q, e, near, K, n, code, status, c.probe, inserted);
+    if (newi < 0) return false;
+    if (e.flags & 4) { sol = newi; status = TRRT_OK_FOUND; return false; }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// schedule 1: cooperative, one iteration at a time
+// ---------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
+    const Group<G> g;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    if (q >= a.nq) return; // whole groups leave together
+    const int K = a.K;
+    RrtQuery Q;
+    rrt_setup<G>(a, q, g, Q);
+    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND;
+    int k;
+    for (k = 1; k < K; k++) {
+        const int it = k - 1;
+        const int sx = __ldg(Q.sxy + 2 * it), sy = __ldg(Q.sxy + 2 * it + 1);
+        const double qx = (double)sx, qy = (double)sy;
+        const double qth = standardangle(__ldg(Q.sth + it));
+        int code, near = -1, newi = -1;
+        bool go = true;
+        if (!Q.m.freespace(sx, sy)) code = TRRT_IT_QRAND_BLOCKED;                                            // rrt.py:148
+        else if (tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, qx, qy, qth, c.probe) >= 0) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
+        else {
+            near = nearest_coop<G>(g, Q.nx, Q.ny, n, qx, qy);
+            c.scan += (unsigned long long)n;
+            Expand e;
+            expand_from<G>(g, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, false, e);
+            bool ins;
+            go = rrt_commit<G>(g, Q, e, near, K, n, nlos, sol, status, code, newi, c, ins);
+        }
+        if (g.gl == 0) {
+            if (Q.it_near) Q.it_near[it] = near;
+            if (Q.it_new) Q.it_new[it] = newi;
+            if (Q.it_code) Q.it_code[it] = (uint8_t)code;
+        }
+        if (!go) {
+            if (status == TRRT_OK_FOUND) k++;
+            break;
+        }
+    }
+    rrt_finish<G>(a, q, g, Q, K, k - 1, n, sol, status, nlos, c);
+}
+
+// ---------------------------------------------------------------------------
+// schedule 0: speculative window of G iterations (see the header comment)
+// ---------------------------------------------------------------------------
+struct __align__(8) SpecRec {
+    Expand e;
+    double bd; // squared distance of the snapshot nearest
+    int near;  // snapshot nearest
+    int pre;   // TRRT_IT_QRAND_BLOCKED, TRRT_IT_NOT_RUN (lane beyond the last iteration) or -1
+};
+
+template <int G>
+__global__ void __launch_bounds__(128) rrt_kernel_spec(const RrtDev a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SpecRec *recs = reinterpret_cast<SpecRec *>(smem_raw) + (threadIdx.x - (threadIdx.x & (G - 1))); // this group's G records
+    const Group<G> g;
+    const Group<1> solo;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    if (q >= a.nq) return;
+    const int K = a.K;
+    RrtQuery Q;
+    rrt_setup<G>(a, q, g, Q);
+    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND;
+    int iters = 0;
+    bool running = true;
+    for (int k0 = 0; k0 < K - 1 && running; k0 += G) {
+        const int n0 = n;
+        // ---------------- phase A: lane j expands iteration k0 + j against the snapshot [0, n0)
+        {
+            const int it = k0 + g.gl;
+            SpecRec r;
+            r.pre = -1; r.near = -1; r.bd = INFINITY;
+            r.e.code = TRRT_IT_NOT_RUN; r.e.flags = 0; r.e.lospx = r.e.arcpx = r.e.arcang = r.e.drive = 0;
+            int sx = 0, sy = 0;
+            double qth = 0;
+            bool live = it < K - 1;
+            if (live) {
+                sx = __ldg(Q.sxy + 2 * it); sy = __ldg(Q.sxy + 2 * it + 1);
+                qth = standardangle(__ldg(Q.sth + it));
+                if (!Q.m.freespace(sx, sy)) { r.pre = TRRT_IT_QRAND_BLOCKED; live = false; } // rrt.py:148
+            } else r.pre = TRRT_IT_NOT_RUN;
+            const double qx = (double)sx, qy = (double)sy;
+            // private nearest scan; node loads are uniform across the warp (broadcast)
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            {
+                int i = 0;
+                for (; i + 3 < n0; i += 4) {
+                    double x0 = Q.nx[i], y0 = Q.ny[i], x1 = Q.nx[i + 1], y1 = Q.ny[i + 1];
+                    double x2 = Q.nx[i + 2], y2 = Q.ny[i + 2], x3 = Q.nx[i + 3], y3 = Q.ny[i + 3];
+                    double dx, dy, d;
+                    dx = qx - x0; dy = qy - y0; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i; }
+                    dx = qx - x1; dy = qy - y1; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 1; }
+                    dx = qx - x2; dy = qy - y2; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 2; }
+                    dx = qx - x3; dy = qy - y3; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 3; }
+                }
+                for (; i < n0; i++) {
+                    double dx = qx - Q.nx[i], dy = qy - Q.ny[i];
+                    double d = dx * dx + dy * dy;
+                    if (d < bd) { bd = d; bi = i; }
+                }
+            }
+            r.bd = bd; r.near = bi;
+            if (live) expand_from<1>(solo, Q.m, a.P, Q.nx[bi], Q.ny[bi], Q.nth[bi], qx, qy, qth, Q.gx, Q.gy, Q.gth, G > 1, r.e);
+            recs[g.gl] = r;
+        }
+        g.sync();
+        // curved edges with many candidate pixels: rasterise them with the whole group, one after the other
+        if (G > 1) {
+            bool pending = (recs[g.gl].pre == -1) && (recs[g.gl].e.flags & (1 << 8));
+            unsigned todo = g.ballot(pending);
+            while (todo) {
+                int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const SpecRec &rj = recs[j];
+                unsigned long long apx = 0, aang = 0;
+                bool blocked = arc_blocked<G>(g, Q.m, Q.nx[rj.near], Q.ny[rj.near], rj.e.wx, rj.e.wy, rj.e.usteer, rj.e.iccx, rj.e.iccy, rj.e.rad,
+                                              &apx, &aang);
+                apx = g.sum(apx); aang = g.sum(aang);
+                g.sync();
+                if (g.gl == j) {
+                    recs[j].e.code = blocked ? TRRT_IT_ARC_BLOCKED : EX_ACCEPT;
+                    recs[j].e.arcpx = (int)apx; recs[j].e.arcang = (int)aang;
+                    recs[j].e.flags &= ~(1 << 8);
+                }
+                g.sync();
+            }
+        }
+        // ---------------- phase B: commit in iteration order
+        double newx = 0, newy = 0; // lane i keeps the i-th node inserted in this window
+        int n_new = 0;
+        for (int j = 0; j < G; j++) {
+            const int it = k0 + j;
+            if (it >= K - 1) break;
+            const SpecRec &rj = recs[j];
+            int code = rj.pre, near = -1, newi = -1;
+            bool go = true;
+            if (code != TRRT_IT_QRAND_BLOCKED) {
+                const int sx = __ldg(Q.sxy + 2 * it), sy = __ldg(Q.sxy + 2 * it + 1);
+                const double qx = (double)sx, qy = (double)sy;
+                const double qth = standardangle(__ldg(Q.sth + it));
+                if (tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, qx, qy, qth, c.probe) >= 0) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
+                else {
+                    // correct the snapshot nearest against the nodes inserted earlier in this window
+                    double d = INFINITY;
+                    int di = 0x7fffffff;
+                    if (g.gl < n_new) { double dx = qx - newx, dy = qy - newy; d = dx * dx + dy * dy; di = n0 + g.gl; }
+                    g.min_di(d, di);
+                    c.scan += (unsigned long long)n;
+                    bool ins = false;
+                    Expand e;
+                    if (d < rj.bd) { // a node of this window is strictly nearer: redo the iteration from it
+                        near = di;
+                        expand_from<G>(g, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, false, e);
+                    } else {
+                        near = rj.near;
+                        e = rj.e;
+                    }
+                    go = rrt_commit<G>(g, Q, e, near, K, n, nlos, sol, status, code, newi, c, ins);
+                    if (ins && g.gl == n_new) { newx = e.wx; newy = e.wy; }
+                    if (ins) n_new++;
+                }
+            }
+            if (g.gl == 0) {
+                if (Q.it_near) Q.it_near[it] = near;
+                if (Q.it_new) Q.it_new[it] = newi;
+                if (Q.it_code) Q.it_code[it] = (uint8_t)code;
+            }
+            iters = it + 1;
+            if (!go) {
+                if (status != TRRT_OK_FOUND) iters = it; // the iteration that raises is not counted
+                running = false;
+                break;
+            }
+        }
+        g.sync();
+    }
+    rrt_finish<G>(a, q, g, Q, K, iters, n, sol, status, nlos, c);
+}
+
+} // namespace trrt

@@ -154,7 +154,7 @@ class Planner:
 
     # ------------------------------------------------------------------ K2
     def rrt(self, starts, goals, sample_xy, sample_th, K=None, params=None, map_id=None, logs=False, want_u=True,
-            counters=False, lanes=0):
+            counters=False, lanes=0, schedule=0):
         """rrt.rrt for a batch.  starts/goals float64 [q,3] (x, y, theta_deg); sample_xy int32 [q,K-1,2];
         sample_th float64 [q,K-1].  K = builtins.K (node capacity; K-1 iterations)."""
         P = params or self.params
@@ -192,7 +192,7 @@ class Planner:
             g = self.grid
             ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
             a = _lib.CRrtArgs(d_bits=g.bits.data_ptr(), n_maps=g.n_maps, H=g.H, W=g.W, d_map_id=ptr(mid),
-                              params=P.to_c(), n_queries=nq, K=K, lanes_per_query=int(lanes),
+                              params=P.to_c(), n_queries=nq, K=K, lanes_per_query=int(lanes), schedule=int(schedule),
                               d_start=starts.data_ptr(), d_goal=goals.data_ptr(), d_sample_xy=sample_xy.data_ptr(),
                               d_sample_th=sample_th.data_ptr(), d_node_x=res.node_x.data_ptr(),
                               d_node_y=res.node_y.data_ptr(), d_node_th=res.node_theta.data_ptr(),
