@@ -662,8 +662,8 @@ static int rrt_tsize(int K) {
     return t;
 }
 size_t trrt_rrt_workspace_bytes(int64_t n_queries, int32_t K) {
-    if (n_queries <= 0 || K <= 0) return 16;
-    return (size_t)n_queries * (size_t)rrt_tsize(K) * sizeof(int32_t) + 16;
+    if (n_queries <= 0 || K <= 0) return 256;
+    return 256 + (size_t)n_queries * (size_t)rrt_tsize(K) * sizeof(int32_t); // [work counter | hash tables]
 }
 
 static BikeParams to_dev(const trrt_params &p) {
@@ -671,6 +671,9 @@ static BikeParams to_dev(const trrt_params &p) {
     b.thetastar = p.thetastar; b.forwardonly = p.forwardonly; b.bikelength = p.bikelength; b.leftconstraint = p.leftconstraint;
     b.rightconstraint = p.rightconstraint; b.frontclearance = p.frontclearance; b.maxdrivedist = p.maxdrivedist;
     b.tol_xy = p.tol_xy; b.tol_ang = p.tol_ang; b.weightxy = p.weightxy;
+    // host evaluation of the device's own rot_make(): bit-identical (trrt_libm.h, no contraction on either side)
+    b.r90 = rot_make(90.0); b.rm90 = rot_make(-90.0); b.r180 = rot_make(180.0);
+    b.rleft = rot_make(p.leftconstraint); b.rright = rot_make(p.rightconstraint);
     return b;
 }
 
@@ -696,7 +699,7 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         return TRRT_ERR_INVALID_ARGUMENT;
     if (A.d_los_log && !A.d_n_los) return TRRT_ERR_INVALID_ARGUMENT;
     if (A.work_bytes < trrt_rrt_workspace_bytes(A.n_queries, A.K)) return TRRT_ERR_WORKSPACE_TOO_SMALL;
-    if ((uintptr_t)A.d_work & 3) return TRRT_ERR_INVALID_ARGUMENT;
+    if ((uintptr_t)A.d_work & 7) return TRRT_ERR_INVALID_ARGUMENT;
     int G = A.lanes_per_query != 0 ? A.lanes_per_query : 32; // one warp per query unless told otherwise
     RrtDev d;
     d.bits = A.d_bits; d.H = A.H; d.W = A.W; d.wpr = (A.W + 31) / 32; d.map_id = A.d_map_id; d.P = to_dev(A.params);
@@ -705,7 +708,8 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
     d.n_nodes = A.d_n_nodes; d.sol = A.d_sol; d.status = A.d_status; d.iters = A.d_iters;
     d.it_near = A.d_it_near; d.it_new = A.d_it_new; d.it_code = A.d_it_code; d.los_log = A.d_los_log; d.n_los = A.d_n_los;
     d.counters = (unsigned long long *)A.d_counters;
-    d.tab = (int32_t *)A.d_work; d.tsize = rrt_tsize(A.K);
+    d.next_query = (unsigned long long *)A.d_work;
+    d.tab = (int32_t *)((char *)A.d_work + 256); d.tsize = rrt_tsize(A.K);
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 128;
     int64_t blocks = (A.n_queries * G + threads - 1) / threads;
@@ -719,17 +723,27 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         case 32: rrt_kernel_coop<32><<<(unsigned)blocks, threads, 0, st>>>(d); break;
         default: return TRRT_ERR_INVALID_ARGUMENT;
         }
-    } else if (A.schedule == 0) { // speculative window of G iterations
+    } else if (A.schedule == 0) { // speculative window of G iterations, persistent groups
         const size_t smem = threads * sizeof(SpecRec);
+        CUDA_TRY(cudaMemsetAsync(d.next_query, 0, sizeof(unsigned long long), st));
+        const void *fn = nullptr;
         switch (G) {
-        case 1: rrt_kernel_spec<1><<<(unsigned)blocks, threads, smem, st>>>(d); break;
-        case 2: rrt_kernel_spec<2><<<(unsigned)blocks, threads, smem, st>>>(d); break;
-        case 4: rrt_kernel_spec<4><<<(unsigned)blocks, threads, smem, st>>>(d); break;
-        case 8: rrt_kernel_spec<8><<<(unsigned)blocks, threads, smem, st>>>(d); break;
-        case 16: rrt_kernel_spec<16><<<(unsigned)blocks, threads, smem, st>>>(d); break;
-        case 32: rrt_kernel_spec<32><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+        case 1: fn = (const void *)rrt_kernel_spec<1>; break;
+        case 2: fn = (const void *)rrt_kernel_spec<2>; break;
+        case 4: fn = (const void *)rrt_kernel_spec<4>; break;
+        case 8: fn = (const void *)rrt_kernel_spec<8>; break;
+        case 16: fn = (const void *)rrt_kernel_spec<16>; break;
+        case 32: fn = (const void *)rrt_kernel_spec<32>; break;
         default: return TRRT_ERR_INVALID_ARGUMENT;
         }
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+        if (per_sm < 1) per_sm = 1;
+        int64_t resident = (int64_t)sm_count() * per_sm; // one full wave; groups loop over the queries
+        if (blocks > resident) blocks = resident;
+        RrtDev *dp = &d;
+        void *kargs[] = {(void *)dp};
+        CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
     } else return TRRT_ERR_INVALID_ARGUMENT;
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;

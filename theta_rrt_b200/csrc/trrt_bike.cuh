@@ -15,9 +15,18 @@ namespace trrt {
 
 #define TRRT_PI 3.141592653589793 /* np.pi */
 
+// Rotation about z by a fixed angle: the matrix scipy's Rotation.apply builds (m11 == m00).
+struct Rot {
+    double m00, m01, m10;
+};
+
 struct BikeParams {
     int thetastar, forwardonly;
     double bikelength, leftconstraint, rightconstraint, frontclearance, maxdrivedist, tol_xy, tol_ang, weightxy;
+    // from_euler('z', a) for the angles the reference uses as literals or parameters (rrt.py:333, :412, :280,
+    // :379, :383): built once on the host by rot_make(), i.e. by the very code the device would run, so the
+    // kernels save five sin/cos evaluations per steer without changing a bit of the result
+    Rot r90, rm90, r180, rleft, rright;
 };
 
 // rrt.py:9-14
@@ -33,16 +42,30 @@ __device__ __forceinline__ void quat_z(double deg, double &z, double &w) {
     tl_sincos(h, &z, &w);
 }
 
+// Rotation.from_euler('z',deg,degrees=True).as_matrix(), the entries apply() needs
+__host__ __device__ __forceinline__ Rot rot_from_quat(double z, double w) {
+    double z2 = z * z, w2 = w * w, zw = z * w;
+    Rot R;
+    R.m00 = -z2 + w2;
+    R.m01 = 2 * (0.0 - zw);
+    R.m10 = 2 * (0.0 + zw);
+    return R;
+}
+__host__ __device__ __forceinline__ Rot rot_make(double deg) {
+    double z, w;
+    double h = (deg * (TRRT_PI / 180.0)) / 2.0;
+    tl_sincos(h, &z, &w);
+    return rot_from_quat(z, w);
+}
+// Rotation.apply([vx,vy,0])[:2] (the compiled backend contracts the dot products)
+__device__ __forceinline__ void rot_apply(const Rot &R, double vx, double vy, double &ox, double &oy) {
+    ox = fma(R.m00, vx, R.m01 * vy);
+    oy = fma(R.m10, vx, R.m00 * vy);
+}
 // Rotation.from_euler('z',deg,degrees=True).apply([vx,vy,0])[:2]
 __device__ __noinline__ void rotz(double deg, double vx, double vy, double &ox, double &oy) {
-    double z, w;
-    quat_z(deg, z, w);
-    double z2 = z * z, w2 = w * w, zw = z * w;
-    double m00 = -z2 + w2;
-    double m01 = 2 * (0.0 - zw);
-    double m10 = 2 * (0.0 + zw);
-    ox = fma(m00, vx, m01 * vy);
-    oy = fma(m10, vx, m00 * vy);
+    Rot R = rot_make(deg);
+    rot_apply(R, vx, vy, ox, oy);
 }
 
 // rrt.py:73-77 (np.dot contracts: fma(v1y, v2y, v1x*v2x))
@@ -122,6 +145,7 @@ __device__ __noinline__ double cond2(double a, double b, double c, double d) {
 struct Steer {
     double x, y, theta;                  // landing state
     double steer, iccx, iccy, rad, dist; // u
+    double bfx, bfy;                     // Rz(theta)*[bikelength,0] of the origin bike (rrt.py:328-330), reused by drive()
     bool straight;                       // u = (0, None, None, 1)
 };
 
@@ -148,10 +172,9 @@ __device__ __noinline__ void steer(const BikeParams &P, double ox, double oy, do
     double bisx = ox - gx, bisy = oy - gy;
     double bfx, bfy, bnx, bny, pbx, pby;
     rotz(theta, L, 0.0, bfx, bfy);
-    // r_90 is used three times (rrt.py:333-335,359): build its matrix once
-    double z90, w90;
-    quat_z(90.0, z90, w90);
-    double r00 = -(z90 * z90) + w90 * w90, r01 = 2 * (0.0 - z90 * w90), r10 = 2 * (0.0 + z90 * w90);
+    o.bfx = bfx; o.bfy = bfy;
+    // r_90 (rrt.py:333-335,359) is a literal angle: matrix precomputed in P
+    const double r00 = P.r90.m00, r01 = P.r90.m01, r10 = P.r90.m10;
     bnx = fma(r00, bfx, r01 * bfy); bny = fma(r10, bfx, r00 * bfy);
     pbx = fma(r00, bisx, r01 * bisy); pby = fma(r10, bisx, r00 * bisy);
     double a1, b1, c1, a2, b2, c2, ix, iy;
@@ -176,8 +199,8 @@ __device__ __noinline__ void steer(const BikeParams &P, double ox, double oy, do
     }
     if (steerangle < P.leftconstraint || steerangle > P.rightconstraint) {
         double fnx = 0, fny = 0;
-        if (steerangle < P.leftconstraint) { steerangle = P.leftconstraint; rotz(steerangle, bnx, bny, fnx, fny); }
-        if (steerangle > P.rightconstraint) { steerangle = P.rightconstraint; rotz(steerangle, bnx, bny, fnx, fny); }
+        if (steerangle < P.leftconstraint) { steerangle = P.leftconstraint; rot_apply(P.rleft, bnx, bny, fnx, fny); }
+        if (steerangle > P.rightconstraint) { steerangle = P.rightconstraint; rot_apply(P.rright, bnx, bny, fnx, fny); }
         linefrompoints(pvx, pvy, pvx + fnx, pvy + fny, a1, b1, c1);
         linefrompoints(ox, oy, ox + bnx, oy + bny, a2, b2, c2);
         if (!solve2(a1, b1, a2, b2, c1, c2, ix, iy) || cond2(a1, b1, a2, b2) > 1000000) {
@@ -191,7 +214,8 @@ __device__ __noinline__ void steer(const BikeParams &P, double ox, double oy, do
     if ((steerangle >= 0 && steerangle < 90) || (steerangle <= -90 && steerangle > -180)) c_ccw = -90;
     else c_ccw = 90;
     double fvx, fvy;
-    rotz(-c_ccw, gx - ix, gy - iy, fvx, fvy);
+    const Rot &rmc = (c_ccw < 0) ? P.r90 : P.rm90; // from_euler('z', -c_ccw): -c_ccw is exactly +90 or -90
+    rot_apply(rmc, gx - ix, gy - iy, fvx, fvy);
     double final_angle = -anglebetween(1, 0, fvx, fvy);
     double mix_angle = P.weightxy * standardangle(final_angle) + (1 - P.weightxy) * standardangle(thetagoal);
     if (point_to_goal_only) mix_angle = anglebetween(1, 0, gx - ox, gy - oy);
@@ -211,15 +235,22 @@ __device__ __noinline__ void steer(const BikeParams &P, double ox, double oy, do
     }
     m2x = ix + m2x; m2y = iy + m2y;
     double ang_goal = anglebetween(1, 0, gx - ix, gy - iy);
-    double diff1 = anglediff(anglebetween(1, 0, m1x - ix, m1y - iy), ang_goal);
-    double diff2 = anglediff(anglebetween(1, 0, m2x - ix, m2y - iy), ang_goal);
+    double diff1, diff2;
+    {   // anglediff(a, ang_goal) twice (rrt.py:435-436): the quaternion of ang_goal is the same both times
+        double sg, cg, s1, c1;
+        quat_z(ang_goal, sg, cg);
+        quat_z(anglebetween(1, 0, m1x - ix, m1y - iy), s1, c1);
+        diff1 = anglediff_q(s1, c1, sg, cg);
+        quat_z(anglebetween(1, 0, m2x - ix, m2y - iy), s1, c1);
+        diff2 = anglediff_q(s1, c1, sg, cg);
+    }
     final_angle = mix_angle;
     double gpx, gpy;
     if (fabs(diff1) < fabs(diff2)) { gpx = m1x; gpy = m1y; }
     else { gpx = m2x; gpy = m2y; final_angle = standardangle(final_angle - 180); }
     if (point_to_goal_only) {
         gpx = m1x; gpy = m1y;
-        rotz(-c_ccw, gpx - ix, gpy - iy, fvx, fvy);
+        rot_apply(rmc, gpx - ix, gpy - iy, fvx, fvy);
         final_angle = -anglebetween(1, 0, fvx, fvy);
     }
     double iox = ox - ix, ioy = oy - iy;
@@ -236,7 +267,7 @@ __device__ __noinline__ void steer(const BikeParams &P, double ox, double oy, do
         if (steerangle < 0) rotz(-mda, iox, ioy, rx, ry);
         else rotz(mda, iox, ioy, rx, ry);
         gpx = rx + ix; gpy = ry + iy;
-        rotz(-c_ccw, gpx - ix, gpy - iy, fvx, fvy);
+        rot_apply(rmc, gpx - ix, gpy - iy, fvx, fvy);
         final_angle = -anglebetween(1, 0, fvx, fvy);
     }
     o.x = gpx; o.y = gpy; o.theta = final_angle;
@@ -244,23 +275,31 @@ __device__ __noinline__ void steer(const BikeParams &P, double ox, double oy, do
 }
 
 // rrt.py:272-304 (dist = u[3], already divided by 3 by the caller, rrt.py:170)
-__device__ __noinline__ void drive(const BikeParams &P, double ox, double oy, double theta, double usteer, double iccx, double iccy,
-                                   double rad, double dist, double &fx, double &fy, double &fang) {
+// bf = Rz(theta)*[bikelength,0] as computed by steer() for the same origin bike (rrt.py:277-279 recomputes it)
+__device__ __noinline__ void drive_bf(const BikeParams &P, double ox, double oy, double bfx, double bfy, double usteer, double iccx,
+                                      double iccy, double rad, double dist, double &fx, double &fy, double &fang) {
     double angle = arclength_to_angle(rad, dist);
-    double bfx, bfy, b1x, b1y;
-    rotz(theta, P.bikelength, 0.0, bfx, bfy);
-    rotz(180.0, bfx, bfy, b1x, b1y);
+    double b1x, b1y;
+    rot_apply(P.r180, bfx, bfy, b1x, b1y);
     bfx = (ox - iccx) + bfx; bfy = (oy - iccy) + bfy;
     b1x = (ox - iccx) + b1x; b1y = (oy - iccy) + b1y;
     double ra = (usteer < 0) ? -angle : angle;
     double tx, ty;
-    rotz(ra, bfx, bfy, tx, ty); bfx = tx; bfy = ty;
-    rotz(ra, b1x, b1y, tx, ty); b1x = tx; b1y = ty;
+    Rot R = rot_make(ra); // the reference applies the same rotation to both points (rrt.py:293-294)
+    rot_apply(R, bfx, bfy, tx, ty); bfx = tx; bfy = ty;
+    rot_apply(R, b1x, b1y, tx, ty); b1x = tx; b1y = ty;
     bfx = iccx + bfx; bfy = iccy + bfy;
     b1x = iccx + b1x; b1y = iccy + b1y;
     double px = 0.5 * (b1x + bfx), py = 0.5 * (b1y + bfy);
     fang = -anglebetween(1, 0, bfx - px, bfy - py);
     fx = px; fy = py;
+}
+// rrt.py:272-304 from scratch (single-step entry point)
+__device__ __forceinline__ void drive(const BikeParams &P, double ox, double oy, double theta, double usteer, double iccx, double iccy,
+                                      double rad, double dist, double &fx, double &fy, double &fang) {
+    double bfx, bfy;
+    rotz(theta, P.bikelength, 0.0, bfx, bfy);
+    drive_bf(P, ox, oy, bfx, bfy, usteer, iccx, iccy, rad, dist, fx, fy, fang);
 }
 
 // Python round(): half to even
@@ -303,31 +342,82 @@ __device__ __noinline__ bool circle_member(long long r, long long a, long long b
 struct ArcTest {
     // inputs of search.getArc (search.py:144-182) for the non-straight case
     double iccx, iccy, usteer;
+    double u1x, u1y, u2x, u2y, n1, n2; // begin - icc, land - icc and their squared lengths
     double beginangle, endangle, diff;
-    double sb, cb, se, ce; // quaternions of beginangle / endangle
-    bool ready;
+    double sb, cb, se, ce; // quaternions of beginangle / endangle (literal path)
+    int diff_lt_180;       // -1 unknown, else the outcome of `diff < 180` (search.py:170)
+    bool ready, literal_ready;
 };
 
-// does getArc keep circle pixel (px, py)?  search.py:161-181
-__device__ __noinline__ bool arc_keeps_pixel(ArcTest &A, double bx, double by, double lx, double ly, long long px, long long py) {
-    if (!A.ready) { // lazily: only needed once a blocked circle pixel is met
-        A.beginangle = anglebetween(1, 0, bx - A.iccx, by - A.iccy);
-        A.endangle = anglebetween(1, 0, lx - A.iccx, ly - A.iccy);
-        quat_z(A.beginangle, A.sb, A.cb);
-        quat_z(A.endangle, A.se, A.ce);
-        double d = (A.usteer < 0) ? anglediff_q(A.sb, A.cb, A.se, A.ce) : anglediff_q(A.se, A.ce, A.sb, A.cb);
-        if (d < 0) d = 360 + d;
-        A.diff = d;
-        A.ready = true;
-    }
-    double pxangle = anglebetween(1, 0, (double)px - A.iccx, (double)py - A.iccy);
+// The reference keeps a circle pixel when the wrapped angle differences `forwardofbegin` and
+// `backwardofgoal` (search.py:163-179) are >= 0.  With a = atan2(-vy, vx) the angle of a vector v
+// (rrt.anglebetween([1,0], v)), the wrapped difference a2 - a1 in (-180, 180] is >= 0 exactly when
+// sin(a2 - a1) = (v2x*v1y - v2y*v1x) / (|v1||v2|) >= 0.  The literal path (atan2, half-angle
+// quaternions, atan2 again) carries ~1e-13 degrees of rounding noise, so whenever |sin| > 1e-9 the sign
+// of the cross product IS the literal outcome and the three atan2 + sin/cos evaluations per blocked
+// pixel are skipped; anything closer to 0 or 180 degrees goes through the literal computation.
+#define TRRT_ARC_GUARD2 1e-18 /* (1e-9)^2, compared against cross^2 / (|v1|^2 |v2|^2) */
+
+__device__ __forceinline__ int cross_sign(double v2x, double v2y, double v1x, double v1y, double n1n2) {
+    // +1 / -1 when sin(a2 - a1) is safely positive / negative, 0 when too close to call
+    double c = v2x * v1y - v2y * v1x;
+    if (!(c * c > TRRT_ARC_GUARD2 * n1n2)) return 0;
+    return c > 0 ? 1 : -1;
+}
+
+__device__ __noinline__ void arc_literal_prepare(ArcTest &A) {
+    A.beginangle = anglebetween(1, 0, A.u1x, A.u1y);
+    A.endangle = anglebetween(1, 0, A.u2x, A.u2y);
+    quat_z(A.beginangle, A.sb, A.cb);
+    quat_z(A.endangle, A.se, A.ce);
+    double d = (A.usteer < 0) ? anglediff_q(A.sb, A.cb, A.se, A.ce) : anglediff_q(A.se, A.ce, A.sb, A.cb);
+    if (d < 0) d = 360 + d;
+    A.diff = d;
+    A.literal_ready = true;
+}
+
+// literal evaluation of one of the two per-pixel differences (which: 0 = forwardofbegin, 1 = backwardofgoal)
+__device__ __noinline__ bool arc_literal_ge0(ArcTest &A, double vx, double vy, int which) {
+    if (!A.literal_ready) arc_literal_prepare(A);
+    double pxangle = anglebetween(1, 0, vx, vy);
     double sp, cp;
     quat_z(pxangle, sp, cp);
-    double fob, bog;
-    if (A.usteer > 0) { fob = anglediff_q(sp, cp, A.sb, A.cb); bog = anglediff_q(A.se, A.ce, sp, cp); }
-    else { fob = anglediff_q(A.sb, A.cb, sp, cp); bog = anglediff_q(sp, cp, A.se, A.ce); }
-    if (A.diff < 180) return (fob >= 0) && (bog >= 0);
-    return (fob >= 0) || (bog >= 0);
+    double d;
+    if (A.usteer > 0) d = (which == 0) ? anglediff_q(sp, cp, A.sb, A.cb) : anglediff_q(A.se, A.ce, sp, cp);
+    else d = (which == 0) ? anglediff_q(A.sb, A.cb, sp, cp) : anglediff_q(sp, cp, A.se, A.ce);
+    return d >= 0;
+}
+
+// does getArc keep circle pixel (px, py)?  search.py:161-181
+__device__ __forceinline__ bool arc_keeps_pixel(ArcTest &A, double bx, double by, double lx, double ly, long long px, long long py) {
+    if (!A.ready) { // lazily: only needed once a blocked circle pixel is met
+        A.u1x = bx - A.iccx; A.u1y = by - A.iccy;
+        A.u2x = lx - A.iccx; A.u2y = ly - A.iccy;
+        A.n1 = A.u1x * A.u1x + A.u1y * A.u1y;
+        A.n2 = A.u2x * A.u2x + A.u2y * A.u2y;
+        // diff = wrapped (endangle - beginangle) for a left turn, (beginangle - endangle) otherwise, in [0, 360)
+        int sd = (A.usteer < 0) ? cross_sign(A.u2x, A.u2y, A.u1x, A.u1y, A.n1 * A.n2) : cross_sign(A.u1x, A.u1y, A.u2x, A.u2y, A.n1 * A.n2);
+        A.diff_lt_180 = (sd == 0) ? -1 : (sd > 0 ? 1 : 0);
+        A.ready = true;
+    }
+    const double vx = (double)px - A.iccx, vy = (double)py - A.iccy;
+    const double nv = vx * vx + vy * vy;
+    int sf, sb;
+    if (A.usteer > 0) { // forwardofbegin = begin - px, backwardofgoal = px - end
+        sf = cross_sign(A.u1x, A.u1y, vx, vy, A.n1 * nv);
+        sb = cross_sign(vx, vy, A.u2x, A.u2y, A.n2 * nv);
+    } else {            // forwardofbegin = px - begin, backwardofgoal = end - px
+        sf = cross_sign(vx, vy, A.u1x, A.u1y, A.n1 * nv);
+        sb = cross_sign(A.u2x, A.u2y, vx, vy, A.n2 * nv);
+    }
+    const bool fob = (sf != 0) ? (sf > 0) : arc_literal_ge0(A, vx, vy, 0);
+    const bool bog = (sb != 0) ? (sb > 0) : arc_literal_ge0(A, vx, vy, 1);
+    if (A.diff_lt_180 < 0) {
+        if (!A.literal_ready) arc_literal_prepare(A);
+        A.diff_lt_180 = (A.diff < 180) ? 1 : 0;
+    }
+    if (A.diff_lt_180) return fob && bog;
+    return fob || bog;
 }
 
 // number of candidate pixels arc_blocked() would enumerate for this circle (rows in range x 2 mirrors)
@@ -362,7 +452,7 @@ __device__ __noinline__ bool arc_blocked_impl(const Group<G> &g, const Grid &m, 
     const T xc = (T)(sizeof(T) == 4 ? (xc_ > lim ? lim : (xc_ < -lim ? -lim : xc_)) : xc_);
     const T yc = (T)(sizeof(T) == 4 ? (yc_ > lim ? lim : (yc_ < -lim ? -lim : yc_)) : yc_);
     ArcTest A;
-    A.iccx = iccx; A.iccy = iccy; A.usteer = usteer; A.ready = false;
+    A.iccx = iccx; A.iccy = iccy; A.usteer = usteer; A.ready = false; A.literal_ready = false;
     bool hit = false;
     const T tmax = (T)circle_tmax(r_);
     const T rr = r * r;

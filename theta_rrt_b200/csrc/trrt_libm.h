@@ -44,21 +44,23 @@
 #define TL_PIO2 1.570796326794896558
 #define TL_PIO2_LO 6.123233995736765886e-17
 
-/* sin on [-pi/4, pi/4], x + y is the reduced argument (y = tail) */
+/* sin on [-pi/4, pi/4], x + y is the reduced argument (y = tail).
+   Polynomials are evaluated with explicit fma() (Horner): same bits on host and device, half the
+   instructions of separate multiply/add. */
 TL_FN double tl_ksin(double x, double y) {
     const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
                  S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
                  S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
     double z = x * x;
-    double zl = fma(x, x, -z);          /* x*x = z + zl exactly */
+    double zl = fma(x, x, -z);                 /* x*x = z + zl exactly */
     double v = z * x;
-    double vl = fma(z, x, -v) + x * zl; /* x^3 = v + vl (to ~2^-106) */
-    double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
-    double t1 = S1 * v;                 /* leading correction -x^3/6 */
-    double t1l = fma(S1, v, -t1) + S1 * vl;
+    double vl = fma(x, zl, fma(z, x, -v));     /* x^3 = v + vl (to ~2^-106) */
+    double r = fma(z, fma(z, fma(z, fma(z, S6, S5), S4), S3), S2);
+    double t1 = S1 * v;                        /* leading correction -x^3/6 */
+    double t1l = fma(S1, vl, fma(S1, v, -t1));
     /* tail terms: y*(1 - z/2) + x^5 * r */
-    double small = (y - z * (0.5 * y - v * r)) + t1l;
-    double s = x + t1;                  /* |x| >= |t1| : Fast2Sum */
+    double small = fma(-z, fma(-v, r, 0.5 * y), y) + t1l;
+    double s = x + t1;                         /* |x| >= |t1| : Fast2Sum */
     double se = t1 - (s - x);
     return s + (se + small);
 }
@@ -69,11 +71,12 @@ TL_FN double tl_kcos(double x, double y) {
                  C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
                  C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
     double z = x * x;
-    double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    double zl = fma(x, x, -z);
+    double r = z * fma(z, fma(z, fma(z, fma(z, fma(z, C6, C5), C4), C3), C2), C1);
     double hz = 0.5 * z;
     double w = 1.0 - hz;
-    double zl = fma(x, x, -z);
-    return w + (((1.0 - w) - hz) + (z * r - (x * y + 0.5 * zl))); /* 1 - hz carried exactly as w + ((1-w)-hz) */
+    double tail = fma(z, r, -fma(x, y, 0.5 * zl));
+    return w + (((1.0 - w) - hz) + tail);      /* 1 - hz carried exactly as w + ((1-w)-hz) */
 }
 
 /* reduce x to y0 + y1 in [-pi/4, pi/4], return quadrant (mod 4 meaningful) */
@@ -83,7 +86,7 @@ TL_FN int tl_rem_pio2(double x, double *y0, double *y1) {
     const double P2 = 6.07710050630396597660e-11, P2T = 2.02226624879595063154e-21;
     const double P3 = 2.02226624871116645580e-21, P3T = 8.47842766036889956997e-32;
     double fn = rint(x * INVPIO2);
-    double r = x - fn * P1; /* exact for |fn| < 2^20 */
+    double r = fma(-fn, P1, x); /* fn*P1 is exact for |fn| < 2^20 (P1 has 33 bits), so this is x - fn*P1 */
     double w = fn * P1T;
     double y = r - w;
     /* cancellation check: redo with more bits of pi/2 when the result is small */
@@ -109,24 +112,21 @@ TL_FN int tl_rem_pio2(double x, double *y0, double *y1) {
 
 TL_ENTRY void tl_sincos(double x, double *s, double *c) {
     double ax = fabs(x);
-    if (!(ax < 1.0e300)) { /* inf / nan / absurd */
-        *s = x - x; *c = x - x; return;
+    double y0 = x, y1 = 0.0;
+    int n = 0;
+    if (ax > 0.78539816339744827900) {
+        if (!(ax < 1.0e300)) { /* inf / nan / absurd */
+            *s = x - x; *c = x - x; return;
+        }
+        n = tl_rem_pio2(x, &y0, &y1);
+    } else if (ax < 7.450580596923828125e-09 /* 2^-27 */) {
+        *s = x; *c = 1.0; return;
     }
-    if (ax <= 0.78539816339744827900) {
-        if (ax < 7.450580596923828125e-09 /* 2^-27 */) { *s = x; *c = 1.0; return; }
-        *s = tl_ksin(x, 0.0);
-        *c = tl_kcos(x, 0.0);
-        return;
-    }
-    double y0, y1;
-    int n = tl_rem_pio2(x, &y0, &y1);
     double ks = tl_ksin(y0, y1), kc = tl_kcos(y0, y1);
-    switch (n) {
-    case 0: *s = ks; *c = kc; break;
-    case 1: *s = kc; *c = -ks; break;
-    case 2: *s = -ks; *c = -kc; break;
-    default: *s = -kc; *c = ks; break;
-    }
+    double ss = (n & 1) ? kc : ks, cc = (n & 1) ? ks : kc;
+    /* quadrant signs: n=0 (s,c) n=1 (c,-s) n=2 (-s,-c) n=3 (-c,s) */
+    *s = (n & 2) ? -ss : ss;
+    *c = ((n + 1) & 2) ? -cc : cc;
 }
 
 /* odd minimax polynomial for atan(t) - t on |t| <= 7/16 (fdlibm aT[]) */
@@ -140,13 +140,13 @@ TL_FN double tl_atan_poly(double t) {
     double z = t * t;
     double zl = fma(t, t, -z);
     double w = z * z;
-    double s1 = z * (A0 + w * (A2 + w * (A4 + w * (A6 + w * (A8 + w * A10)))));
-    double s2 = w * (A1 + w * (A3 + w * (A5 + w * (A7 + w * A9))));
-    return t * ((s1 + s2) + A0 * zl); /* atan(t) = t - this */
+    double s1 = z * fma(w, fma(w, fma(w, fma(w, fma(w, A10, A8), A6), A4), A2), A0);
+    double s2 = w * fma(w, fma(w, fma(w, fma(w, A9, A7), A5), A3), A1);
+    return t * fma(A0, zl, s1 + s2); /* atan(t) = t - this */
 }
 
-/* atan2 for finite, non-NaN arguments and the IEEE special cases numpy/libm define */
-TL_ENTRY double tl_atan2(double y, double x) {
+/* zeros, infinities, NaN: the values numpy / C99 define */
+TL_FN double tl_atan2_special(double y, double x) {
     if (x != x || y != y) return x + y;
     double ay = fabs(y), ax = fabs(x);
     int yneg = signbit(y) ? 1 : 0, xneg = signbit(x) ? 1 : 0;
@@ -163,8 +163,13 @@ TL_ENTRY double tl_atan2(double y, double x) {
         if (xneg) return yneg ? -TL_PI : TL_PI;
         return yneg ? -0.0 : 0.0;
     }
-    if (isinf(ay)) return yneg ? -TL_PIO2 : TL_PIO2;
+    return yneg ? -TL_PIO2 : TL_PIO2; /* |y| = inf, x finite */
+}
 
+TL_ENTRY double tl_atan2(double y, double x) {
+    double ay = fabs(y), ax = fabs(x);
+    /* one test for every special case: both magnitudes must be finite and non-zero */
+    if (!(ax > 0.0 && ay > 0.0 && ax < INFINITY && ay < INFINITY)) return tl_atan2_special(y, x);
     /* first-quadrant angle a = atan(ay/ax) by angle addition against c in {0, 1/2, 1, 2, inf}:
        atan(ay/ax) = atan(c) + atan(t), t = (ay - c*ax)/(ax + c*ay), |t| <= 7/16.
        c*ax, c*ay and the numerator are exact (Sterbenz); the denominator is carried as dh + dl. */
@@ -185,26 +190,27 @@ TL_ENTRY double tl_atan2(double y, double x) {
         double bb = dh - ax;             /* TwoSum(ax, cy) */
         dl = (ax - (dh - bb)) + (cy - bb);
     }
-    double t = num / dh;
-    double e = (fma(-t, dh, num) - t * dl) / dh; /* NUM/DEN = t + e */
+    /* one division: t approximates NUM/DEN, e is the remainder of the exact quotient */
+    double rdh = 1.0 / dh;
+    double t = num * rdh;
+    double e = fma(-t, dl, fma(-t, dh, num)) * rdh; /* NUM/(dh+dl) = t + e */
     double p = tl_atan_poly(t);
-    /* atan(t + e) ~= t - p + e*(1 - t*t) (|e| <= ~ulp(t), |t| <= 7/16) */
-    double small = (e * (1.0 - t * t) - p) + lo;
+    /* atan(t + e) ~= t - p + e*(1 - t*t) (|e| <= ~2 ulp(t), |t| <= 7/16) */
+    double small = fma(e, fma(-t, t, 1.0), -p) + lo;
     double s, rest; /* first-quadrant result = s + rest, |rest| << |s| */
     if (hi == 0.0) { s = t; rest = small; }
     else {
         s = hi + t;                      /* |hi| >= |t| : Fast2Sum */
         rest = (t - (s - hi)) + small;
     }
-    if (!xneg) {
-        double a = s + rest;
-        return yneg ? -a : a;
+    double r;
+    if (x > 0.0) r = s + rest;
+    else { /* second/third quadrant: pi - (s + rest) with the low word of pi */
+        double u = TL_PI - s;            /* |pi| >= |s| : Fast2Sum */
+        double ue = (TL_PI - u) - s;
+        r = u + ((ue + TL_PI_LO) - rest);
     }
-    /* second/third quadrant: pi - (s + rest) with the low word of pi */
-    double u = TL_PI - s;                /* |pi| >= |s| : Fast2Sum */
-    double ue = (TL_PI - u) - s;
-    double r = u + ((ue + TL_PI_LO) - rest);
-    return yneg ? -r : r;
+    return (y < 0.0) ? -r : r;
 }
 
 #endif /* TRRT_LIBM_H */

@@ -43,6 +43,7 @@ struct RrtDev {
     unsigned long long *counters;
     int32_t *tab; // [nq][tsize] open-addressing index table for the `in G.keys()` tests
     int tsize;
+    unsigned long long *next_query; // work counter of the persistent speculative kernel (zeroed by the launcher)
 };
 
 __device__ __forceinline__ unsigned hash3(double x, double y, double t) {
@@ -109,16 +110,18 @@ __device__ __noinline__ void expand_from(const Group<GA> &ga, const Grid &m, con
     unsigned long long px = 0;
     int nlos = 0;
     bool ok = m.inb(trunc_ll(e.wx), trunc_ll(e.wy));
+    Rot Rw;
+    if (ok) Rw = rot_make(e.wth); // bike_clear and front_of_bike_clear rotate by the same heading (rrt.py:210,217)
     if (ok) {
         double bx, by;
-        rotz(e.wth, P.bikelength, 0.0, bx, by);
+        rot_apply(Rw, P.bikelength, 0.0, bx, by);
         ok = los_group<GA>(ga, m, trunc_ll(e.wx), trunc_ll(e.wy), trunc_ll(bx + e.wx), trunc_ll(by + e.wy), &px);
         if (ok) e.flags |= 1 << 6;
         nlos = 1;
     }
     if (ok) {
         double bx, by;
-        rotz(e.wth, P.bikelength * P.frontclearance, 0.0, bx, by);
+        rot_apply(Rw, P.bikelength * P.frontclearance, 0.0, bx, by);
         ok = los_group<GA>(ga, m, trunc_ll(e.wx), trunc_ll(e.wy), trunc_ll(bx + e.wx), trunc_ll(by + e.wy), &px);
         if (ok) e.flags |= 1 << 7;
         nlos = 2;
@@ -128,7 +131,7 @@ __device__ __noinline__ void expand_from(const Group<GA> &ga, const Grid &m, con
     if (!ok) {
         if (s.straight) { e.flags |= 2; e.code = TRRT_IT_NOT_RUN; return; } // rrt.py:170-171 -> TypeError in the reference
         e.udist = s.dist / 3;
-        drive(P, ox, oy, oth, s.steer, s.iccx, s.iccy, s.rad, e.udist, e.wx, e.wy, e.wth);
+        drive_bf(P, ox, oy, s.bfx, s.bfy, s.steer, s.iccx, s.iccy, s.rad, e.udist, e.wx, e.wy, e.wth);
         e.drive = 1;
     }
     // goal test input (rrt.py:191-198) depends only on qnew
@@ -353,15 +356,24 @@ struct __align__(8) SpecRec {
     int pre;   // TRRT_IT_QRAND_BLOCKED, TRRT_IT_NOT_RUN (lane beyond the last iteration) or -1
 };
 
+#ifndef TRRT_SPEC_MIN_BLOCKS
+#define TRRT_SPEC_MIN_BLOCKS 4
+#endif
 template <int G>
-__global__ void __launch_bounds__(128) rrt_kernel_spec(const RrtDev a) {
+__global__ void __launch_bounds__(128, TRRT_SPEC_MIN_BLOCKS) rrt_kernel_spec(const RrtDev a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SpecRec *recs = reinterpret_cast<SpecRec *>(smem_raw) + (threadIdx.x - (threadIdx.x & (G - 1))); // this group's G records
     const Group<G> g;
     const Group<1> solo;
-    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
-    if (q >= a.nq) return;
     const int K = a.K;
+    // persistent groups: queries differ a lot in length (27% of the cfg-3 queries end early), so each group
+    // pulls the next query from a counter instead of owning a fixed one
+    for (;;) {
+    unsigned long long qq = 0;
+    if (g.gl == 0) qq = atomicAdd(a.next_query, 1ull);
+    qq = g.bcast(qq, 0);
+    if (qq >= (unsigned long long)a.nq) break;
+    const int64_t q = (int64_t)qq;
     RrtQuery Q;
     rrt_setup<G>(a, q, g, Q);
     RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -456,7 +468,17 @@ __global__ void __launch_bounds__(128) rrt_kernel_spec(const RrtDev a) {
                     Expand e;
                     if (d < rj.bd) { // a node of this window is strictly nearer: redo the iteration from it
                         near = di;
-                        expand_from<G>(g, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, false, e);
+                        // every lane runs the single-lane expansion on the same inputs (same code as phase A, so it
+                        // is already in the instruction cache); only a big raster is shared out over the group
+                        expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, G > 1, e);
+                        if (G > 1 && (e.flags & (1 << 8))) {
+                            unsigned long long apx = 0, aang = 0;
+                            bool blocked = arc_blocked<G>(g, Q.m, Q.nx[near], Q.ny[near], e.wx, e.wy, e.usteer, e.iccx, e.iccy, e.rad, &apx, &aang);
+                            apx = g.sum(apx); aang = g.sum(aang);
+                            e.code = blocked ? TRRT_IT_ARC_BLOCKED : EX_ACCEPT;
+                            e.arcpx = (int)apx; e.arcang = (int)aang;
+                            e.flags &= ~(1 << 8);
+                        }
                     } else {
                         near = rj.near;
                         e = rj.e;
@@ -481,6 +503,8 @@ __global__ void __launch_bounds__(128) rrt_kernel_spec(const RrtDev a) {
         g.sync();
     }
     rrt_finish<G>(a, q, g, Q, K, iters, n, sol, status, nlos, c);
+    g.sync();
+    } // next query
 }
 
 } // namespace trrt
