@@ -724,7 +724,7 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         default: return TRRT_ERR_INVALID_ARGUMENT;
         }
     } else if (A.schedule == 0) { // speculative window of G iterations, persistent groups
-        const size_t smem = threads * sizeof(SpecRec);
+        const size_t smem = 0;
         CUDA_TRY(cudaMemsetAsync(d.next_query, 0, sizeof(unsigned long long), st));
         const void *fn = nullptr;
         switch (G) {

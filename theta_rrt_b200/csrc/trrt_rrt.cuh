@@ -20,6 +20,7 @@
 //    The committed sequence is exactly the sequential loop.
 #pragma once
 #include "trrt_bike.cuh"
+#include "trrt_lane.cuh"
 
 namespace trrt {
 
@@ -92,12 +93,20 @@ struct Expand {
     int drive;
 };
 
-// Everything after the nearest node is known.  ARC: group used for rays / raster (Group<1> = one lane alone).
-// defer_big_arcs: leave a curved edge with many candidate pixels untested (flag bit 8) for a cooperative pass.
+// Everything after the nearest node is known.  GA lanes share the rays / raster; GA == 1 is one lane working
+// alone (speculative schedule) and takes the single-lane code of trrt_lane.cuh.
+template <int GA>
+__device__ __forceinline__ bool ray_clear(const Group<GA> &ga, const Grid &m, long long ax, long long ay, long long bx, long long by, int *px) {
+    if (GA == 1) return los_lane(m, ax, ay, bx, by, px);
+    unsigned long long p = 0;
+    bool ok = los_group<GA>(ga, m, ax, ay, bx, by, &p);
+    *px += (int)p;
+    return ok;
+}
+
 template <int GA>
 __device__ __noinline__ void expand_from(const Group<GA> &ga, const Grid &m, const BikeParams &P, double ox, double oy, double oth,
-                                            double qx, double qy, double qth, double gx, double gy, double gth, bool defer_big_arcs,
-                                            Expand &e) {
+                                            double qx, double qy, double qth, double gx, double gy, double gth, Expand &e) {
     Steer s;
     steer(P, ox, oy, oth, qx, qy, qth, s);
     e.wx = s.x; e.wy = s.y; e.wth = s.theta;
@@ -107,27 +116,23 @@ __device__ __noinline__ void expand_from(const Group<GA> &ga, const Grid &m, con
     double us = standardangle(s.steer);
     if (us < P.leftconstraint || us > P.rightconstraint) { e.code = TRRT_IT_STEER_CONSTRAINT; return; } // rrt.py:166
     // clearance (rrt.py:169): valid, bike_clear, front_of_bike_clear with short-circuit
-    unsigned long long px = 0;
     int nlos = 0;
     bool ok = m.inb(trunc_ll(e.wx), trunc_ll(e.wy));
-    Rot Rw;
-    if (ok) Rw = rot_make(e.wth); // bike_clear and front_of_bike_clear rotate by the same heading (rrt.py:210,217)
     if (ok) {
+        const Rot Rw = rot_make(e.wth); // bike_clear and front_of_bike_clear rotate by the same heading (rrt.py:210,217)
         double bx, by;
         rot_apply(Rw, P.bikelength, 0.0, bx, by);
-        ok = los_group<GA>(ga, m, trunc_ll(e.wx), trunc_ll(e.wy), trunc_ll(bx + e.wx), trunc_ll(by + e.wy), &px);
+        ok = ray_clear<GA>(ga, m, trunc_ll(e.wx), trunc_ll(e.wy), trunc_ll(bx + e.wx), trunc_ll(by + e.wy), &e.lospx);
         if (ok) e.flags |= 1 << 6;
         nlos = 1;
-    }
-    if (ok) {
-        double bx, by;
-        rot_apply(Rw, P.bikelength * P.frontclearance, 0.0, bx, by);
-        ok = los_group<GA>(ga, m, trunc_ll(e.wx), trunc_ll(e.wy), trunc_ll(bx + e.wx), trunc_ll(by + e.wy), &px);
-        if (ok) e.flags |= 1 << 7;
-        nlos = 2;
+        if (ok) {
+            rot_apply(Rw, P.bikelength * P.frontclearance, 0.0, bx, by);
+            ok = ray_clear<GA>(ga, m, trunc_ll(e.wx), trunc_ll(e.wy), trunc_ll(bx + e.wx), trunc_ll(by + e.wy), &e.lospx);
+            if (ok) e.flags |= 1 << 7;
+            nlos = 2;
+        }
     }
     e.flags |= nlos << 4;
-    e.lospx = (int)px;
     if (!ok) {
         if (s.straight) { e.flags |= 2; e.code = TRRT_IT_NOT_RUN; return; } // rrt.py:170-171 -> TypeError in the reference
         e.udist = s.dist / 3;
@@ -142,14 +147,13 @@ __device__ __noinline__ void expand_from(const Group<GA> &ga, const Grid &m, con
     // edge collision (rrt.py:173-176)
     bool blocked;
     if (s.straight) {
-        unsigned long long apx = 0;
-        blocked = !los_group<GA>(ga, m, trunc_ll(ox), trunc_ll(oy), trunc_ll(e.wx), trunc_ll(e.wy), &apx);
-        e.arcpx = (int)apx;
+        blocked = !ray_clear<GA>(ga, m, trunc_ll(ox), trunc_ll(oy), trunc_ll(e.wx), trunc_ll(e.wy), &e.arcpx);
+    } else if (GA == 1) {
+        blocked = arc_blocked_lane(m, ox, oy, e.wx, e.wy, s.steer, s.iccx, s.iccy, s.rad, &e.arcpx, &e.arcang);
     } else {
-        if (defer_big_arcs && (s.rad >= 32768.0 || arc_candidates(m, s.iccx, s.iccy, s.rad) > 64)) { e.flags |= 1 << 8; e.code = EX_ACCEPT; return; }
         unsigned long long apx = 0, aang = 0;
         blocked = arc_blocked<GA>(ga, m, ox, oy, e.wx, e.wy, s.steer, s.iccx, s.iccy, s.rad, &apx, &aang);
-        if (GA > 1) { apx = ga.sum(apx); aang = ga.sum(aang); }
+        apx = ga.sum(apx); aang = ga.sum(aang);
         e.arcpx = (int)apx; e.arcang = (int)aang;
     }
     e.code = blocked ? TRRT_IT_ARC_BLOCKED : EX_ACCEPT;
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
             near = nearest_coop<G>(g, Q.nx, Q.ny, n, qx, qy);
             c.scan += (unsigned long long)n;
             Expand e;
-            expand_from<G>(g, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, false, e);
+            expand_from<G>(g, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
             bool ins;
             go = rrt_commit<G>(g, Q, e, near, K, n, nlos, sol, status, code, newi, c, ins);
         }
@@ -348,21 +352,53 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
 
 // ---------------------------------------------------------------------------
 // schedule 0: speculative window of G iterations (see the header comment)
+//
+// Phase A (lane j = iteration k0+j, all lanes in parallel, everything in registers):
+//   sample -> freespace(qrand) -> `qrand in G` probe of the snapshot index -> private nearest scan over the
+//   snapshot -> steer / clearance rays / re-drive / edge raster (expand_from<1>) -> `qnew in G` probe.
+// Phase B (commit, iteration order, uniform control flow): step j only moves a few words out of lane j with
+//   shuffles.  When a step inserts a node, lane j writes it (tree arrays + index) and broadcasts its coordinates;
+//   every lane folds that node into (a) its distance-to-nodes-of-this-window minimum and (b) its two equality
+//   flags, so later steps need neither a reduction nor an index probe.  If a node of the window is strictly nearer
+//   than lane j's snapshot winner (new nodes have higher indices, so ties stay with the snapshot), lane j alone
+//   re-expands its iteration from that node before committing.
 // ---------------------------------------------------------------------------
-struct __align__(8) SpecRec {
-    Expand e;
-    double bd; // squared distance of the snapshot nearest
-    int near;  // snapshot nearest
-    int pre;   // TRRT_IT_QRAND_BLOCKED, TRRT_IT_NOT_RUN (lane beyond the last iteration) or -1
-};
-
 #ifndef TRRT_SPEC_MIN_BLOCKS
 #define TRRT_SPEC_MIN_BLOCKS 4
 #endif
+
+// private fp64 nearest scan over nodes [0, n): every lane of the warp reads the same node (broadcast loads)
+__device__ __forceinline__ void nearest_private(const double *__restrict__ nx, const double *__restrict__ ny, int n, double qx, double qy,
+                                                double &bd_out, int &bi_out) {
+    double bd = INFINITY;
+    int bi = 0x7fffffff;
+    int i = 0;
+#define TRRT_NODE(xv, yv, idx) { double dx = qx - (xv), dy = qy - (yv); double d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = (idx); } }
+    if ((((uintptr_t)nx ^ (uintptr_t)ny) & 15) == 0) { // rows equally aligned: 16-byte loads, two nodes each
+        if (((uintptr_t)nx & 15) != 0 && n > 0) { TRRT_NODE(nx[0], ny[0], 0); i = 1; }
+        const double2 *x2 = reinterpret_cast<const double2 *>(nx + i);
+        const double2 *y2 = reinterpret_cast<const double2 *>(ny + i);
+        const int pairs = (n - i) >> 1;
+        int p = 0;
+        for (; p + 1 < pairs; p += 2) {
+            const double2 xa = x2[p], ya = y2[p], xb = x2[p + 1], yb = y2[p + 1];
+            const int b = i + 2 * p;
+            TRRT_NODE(xa.x, ya.x, b); TRRT_NODE(xa.y, ya.y, b + 1); TRRT_NODE(xb.x, yb.x, b + 2); TRRT_NODE(xb.y, yb.y, b + 3);
+        }
+        if (p < pairs) {
+            const double2 xa = x2[p], ya = y2[p];
+            const int b = i + 2 * p;
+            TRRT_NODE(xa.x, ya.x, b); TRRT_NODE(xa.y, ya.y, b + 1);
+        }
+        i += 2 * pairs;
+    }
+    for (; i < n; i++) TRRT_NODE(nx[i], ny[i], i);
+#undef TRRT_NODE
+    bd_out = bd; bi_out = bi;
+}
+
 template <int G>
 __global__ void __launch_bounds__(128, TRRT_SPEC_MIN_BLOCKS) rrt_kernel_spec(const RrtDev a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SpecRec *recs = reinterpret_cast<SpecRec *>(smem_raw) + (threadIdx.x - (threadIdx.x & (G - 1))); // this group's G records
     const Group<G> g;
     const Group<1> solo;
     const int K = a.K;
@@ -376,120 +412,119 @@ __global__ void __launch_bounds__(128, TRRT_SPEC_MIN_BLOCKS) rrt_kernel_spec(con
     const int64_t q = (int64_t)qq;
     RrtQuery Q;
     rrt_setup<G>(a, q, g, Q);
-    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0};
+    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0}; // scan is kept uniform; the others are lane-private sums, folded at the end
     int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND;
     int iters = 0;
     bool running = true;
     for (int k0 = 0; k0 < K - 1 && running; k0 += G) {
         const int n0 = n;
-        // ---------------- phase A: lane j expands iteration k0 + j against the snapshot [0, n0)
-        {
-            const int it = k0 + g.gl;
-            SpecRec r;
-            r.pre = -1; r.near = -1; r.bd = INFINITY;
-            r.e.code = TRRT_IT_NOT_RUN; r.e.flags = 0; r.e.lospx = r.e.arcpx = r.e.arcang = r.e.drive = 0;
-            int sx = 0, sy = 0;
-            double qth = 0;
-            bool live = it < K - 1;
-            if (live) {
-                sx = __ldg(Q.sxy + 2 * it); sy = __ldg(Q.sxy + 2 * it + 1);
-                qth = standardangle(__ldg(Q.sth + it));
-                if (!Q.m.freespace(sx, sy)) { r.pre = TRRT_IT_QRAND_BLOCKED; live = false; } // rrt.py:148
-            } else r.pre = TRRT_IT_NOT_RUN;
-            const double qx = (double)sx, qy = (double)sy;
-            // private nearest scan; node loads are uniform across the warp (broadcast)
-            double bd = INFINITY;
-            int bi = 0x7fffffff;
-            {
-                int i = 0;
-                for (; i + 3 < n0; i += 4) {
-                    double x0 = Q.nx[i], y0 = Q.ny[i], x1 = Q.nx[i + 1], y1 = Q.ny[i + 1];
-                    double x2 = Q.nx[i + 2], y2 = Q.ny[i + 2], x3 = Q.nx[i + 3], y3 = Q.ny[i + 3];
-                    double dx, dy, d;
-                    dx = qx - x0; dy = qy - y0; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i; }
-                    dx = qx - x1; dy = qy - y1; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 1; }
-                    dx = qx - x2; dy = qy - y2; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 2; }
-                    dx = qx - x3; dy = qy - y3; d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = i + 3; }
-                }
-                for (; i < n0; i++) {
-                    double dx = qx - Q.nx[i], dy = qy - Q.ny[i];
-                    double d = dx * dx + dy * dy;
-                    if (d < bd) { bd = d; bi = i; }
-                }
-            }
-            r.bd = bd; r.near = bi;
-            if (live) expand_from<1>(solo, Q.m, a.P, Q.nx[bi], Q.ny[bi], Q.nth[bi], qx, qy, qth, Q.gx, Q.gy, Q.gth, G > 1, r.e);
-            recs[g.gl] = r;
+        // ---------------- phase A
+        const int my_it = k0 + g.gl;
+        int pre = -1;          // TRRT_IT_QRAND_BLOCKED, TRRT_IT_NOT_RUN (beyond the last iteration) or -1 = live
+        bool q_in_tree = false; // rrt.py:151 against the snapshot (+ nodes of this window, folded in below)
+        int near = -1, exist = -1; // nearest node; index of a tree node equal to qnew, or -1
+        double bd = INFINITY, qx = 0, qy = 0, qth = 0;
+        double wbest = INFINITY; // squared distance to the nearest node inserted earlier in this window
+        int widx = -1;
+        unsigned long long probes = 0;
+        Expand e;
+        e.code = TRRT_IT_NOT_RUN; e.flags = 0; e.lospx = e.arcpx = e.arcang = e.drive = 0;
+        e.wx = e.wy = e.wth = NAN; // never equal to a node
+        if (my_it < K - 1) {
+            const int sx = __ldg(Q.sxy + 2 * my_it), sy = __ldg(Q.sxy + 2 * my_it + 1);
+            qx = (double)sx; qy = (double)sy;
+            qth = standardangle(__ldg(Q.sth + my_it));
+            if (!Q.m.freespace(sx, sy)) pre = TRRT_IT_QRAND_BLOCKED; // rrt.py:148
+            else q_in_tree = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, qx, qy, qth, probes) >= 0;
+        } else pre = TRRT_IT_NOT_RUN;
+        const bool live = (pre == -1) && !q_in_tree;
+        // the scan is executed by the whole warp (lanes without a live sample idle through it)
+        nearest_private(Q.nx, Q.ny, live ? n0 : 0, qx, qy, bd, near);
+        if (live) {
+            expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
+            if (e.code == EX_ACCEPT) exist = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes);
         }
         g.sync();
-        // curved edges with many candidate pixels: rasterise them with the whole group, one after the other
-        if (G > 1) {
-            bool pending = (recs[g.gl].pre == -1) && (recs[g.gl].e.flags & (1 << 8));
-            unsigned todo = g.ballot(pending);
-            while (todo) {
-                int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const SpecRec &rj = recs[j];
-                unsigned long long apx = 0, aang = 0;
-                bool blocked = arc_blocked<G>(g, Q.m, Q.nx[rj.near], Q.ny[rj.near], rj.e.wx, rj.e.wy, rj.e.usteer, rj.e.iccx, rj.e.iccy, rj.e.rad,
-                                              &apx, &aang);
-                apx = g.sum(apx); aang = g.sum(aang);
-                g.sync();
-                if (g.gl == j) {
-                    recs[j].e.code = blocked ? TRRT_IT_ARC_BLOCKED : EX_ACCEPT;
-                    recs[j].e.arcpx = (int)apx; recs[j].e.arcang = (int)aang;
-                    recs[j].e.flags &= ~(1 << 8);
-                }
-                g.sync();
-            }
-        }
         // ---------------- phase B: commit in iteration order
-        double newx = 0, newy = 0; // lane i keeps the i-th node inserted in this window
-        int n_new = 0;
         for (int j = 0; j < G; j++) {
             const int it = k0 + j;
-            if (it >= K - 1) break;
-            const SpecRec &rj = recs[j];
-            int code = rj.pre, near = -1, newi = -1;
+            const int pre_j = g.bcast(pre, j);
+            if (pre_j == TRRT_IT_NOT_RUN) break;
+            int code = pre_j, near_j = -1, newi = -1;
             bool go = true;
-            if (code != TRRT_IT_QRAND_BLOCKED) {
-                const int sx = __ldg(Q.sxy + 2 * it), sy = __ldg(Q.sxy + 2 * it + 1);
-                const double qx = (double)sx, qy = (double)sy;
-                const double qth = standardangle(__ldg(Q.sth + it));
-                if (tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, qx, qy, qth, c.probe) >= 0) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
+            if (pre_j != TRRT_IT_QRAND_BLOCKED) {
+                if (g.bcast((int)q_in_tree, j)) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
                 else {
-                    // correct the snapshot nearest against the nodes inserted earlier in this window
-                    double d = INFINITY;
-                    int di = 0x7fffffff;
-                    if (g.gl < n_new) { double dx = qx - newx, dy = qy - newy; d = dx * dx + dy * dy; di = n0 + g.gl; }
-                    g.min_di(d, di);
-                    c.scan += (unsigned long long)n;
-                    bool ins = false;
-                    Expand e;
-                    if (d < rj.bd) { // a node of this window is strictly nearer: redo the iteration from it
-                        near = di;
-                        // every lane runs the single-lane expansion on the same inputs (same code as phase A, so it
-                        // is already in the instruction cache); only a big raster is shared out over the group
-                        expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, G > 1, e);
-                        if (G > 1 && (e.flags & (1 << 8))) {
-                            unsigned long long apx = 0, aang = 0;
-                            bool blocked = arc_blocked<G>(g, Q.m, Q.nx[near], Q.ny[near], e.wx, e.wy, e.usteer, e.iccx, e.iccy, e.rad, &apx, &aang);
-                            apx = g.sum(apx); aang = g.sum(aang);
-                            e.code = blocked ? TRRT_IT_ARC_BLOCKED : EX_ACCEPT;
-                            e.arcpx = (int)apx; e.arcang = (int)aang;
-                            e.flags &= ~(1 << 8);
+                    if (g.bcast((int)(wbest < bd), j)) {
+                        // a node of this window is strictly nearer: lane j redoes its iteration from it
+                        g.sync(); // nodes written by earlier steps are visible to lane j
+                        if (g.gl == j) {
+                            near = widx;
+                            expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
+                            exist = -1;
+                            if (e.code == EX_ACCEPT) exist = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes);
                         }
-                    } else {
-                        near = rj.near;
-                        e = rj.e;
                     }
-                    go = rrt_commit<G>(g, Q, e, near, K, n, nlos, sol, status, code, newi, c, ins);
-                    if (ins && g.gl == n_new) { newx = e.wx; newy = e.wy; }
-                    if (ins) n_new++;
+                    near_j = g.bcast(near, j);
+                    const int ecode = g.bcast(e.code, j), eflags = g.bcast(e.flags, j);
+                    c.scan += (unsigned long long)n;
+                    const bool mine = g.gl == j;
+                    if (mine) c.steer++;
+                    if (ecode == TRRT_IT_STEER_CONSTRAINT) code = TRRT_IT_STEER_CONSTRAINT;
+                    else {
+                        const int nl = (eflags >> 4) & 3;
+                        if (mine) {
+                            if (Q.los_log) {
+                                if (nl >= 1) Q.los_log[nlos] = (eflags >> 6) & 1;
+                                if (nl >= 2) Q.los_log[nlos + 1] = (eflags >> 7) & 1;
+                            }
+                            c.los += nl; c.lospx += e.lospx; c.arcpx += e.arcpx; c.arcang += e.arcang; c.drive += e.drive;
+                        }
+                        nlos += nl;
+                        if (eflags & 2) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; code = TRRT_IT_NOT_RUN; go = false; }
+                        else if (ecode == TRRT_IT_ARC_BLOCKED) code = TRRT_IT_ARC_BLOCKED;
+                        else { // rrt.py:179-201
+                            int idx = g.bcast(exist, j);
+                            if (idx < 0) {
+                                if (n >= K) { status = TRRT_ERR_CAPACITY; code = TRRT_IT_NOT_RUN; go = false; }
+                                else {
+                                    idx = n++;
+                                    code = TRRT_IT_NEW_NODE;
+                                    if (mine) {
+                                        Q.nx[idx] = e.wx; Q.ny[idx] = e.wy; Q.nth[idx] = e.wth;
+                                        Q.parent[idx] = -1;
+                                        if (Q.uo) for (int t = 0; t < 5; t++) Q.uo[5 * idx + t] = NAN;
+                                        tree_insert(Q.tab, Q.tmask, e.wx, e.wy, e.wth, idx);
+                                    }
+                                    // every lane folds the new node into its window minimum and equality flags
+                                    const double vx = g.bcast(e.wx, j), vy = g.bcast(e.wy, j), vth = g.bcast(e.wth, j);
+                                    if (g.gl > j) {
+                                        const double dx = qx - vx, dy = qy - vy;
+                                        const double d = dx * dx + dy * dy;
+                                        if (d < wbest) { wbest = d; widx = idx; }
+                                        if (qx == vx && qy == vy && qth == vth) q_in_tree = true;
+                                        if (exist < 0 && e.wx == vx && e.wy == vy && e.wth == vth) exist = idx;
+                                    }
+                                }
+                            } else code = TRRT_IT_EXISTING_NODE;
+                            if (go) {
+                                newi = idx;
+                                if (idx != near_j && mine) { // rrt.py:187-188
+                                    Q.parent[idx] = near_j;
+                                    if (Q.uo) {
+                                        const bool st = eflags & 1;
+                                        Q.uo[5 * idx] = e.usteer; Q.uo[5 * idx + 1] = st ? NAN : e.iccx; Q.uo[5 * idx + 2] = st ? NAN : e.iccy;
+                                        Q.uo[5 * idx + 3] = st ? NAN : e.rad; Q.uo[5 * idx + 4] = e.udist;
+                                    }
+                                }
+                                if (eflags & 4) { sol = idx; status = TRRT_OK_FOUND; go = false; }
+                            }
+                        }
+                    }
                 }
             }
-            if (g.gl == 0) {
-                if (Q.it_near) Q.it_near[it] = near;
+            if (g.gl == j) {
+                if (Q.it_near) Q.it_near[it] = near_j;
                 if (Q.it_new) Q.it_new[it] = newi;
                 if (Q.it_code) Q.it_code[it] = (uint8_t)code;
             }
@@ -500,7 +535,13 @@ __global__ void __launch_bounds__(128, TRRT_SPEC_MIN_BLOCKS) rrt_kernel_spec(con
                 break;
             }
         }
-        g.sync();
+        c.probe += probes;
+        g.sync(); // tree and index writes of this window are visible to every lane's next phase A
+    }
+    // fold the lane-private counters
+    if (a.counters) {
+        c.los = g.sum(c.los); c.lospx = g.sum(c.lospx); c.arcpx = g.sum(c.arcpx); c.arcang = g.sum(c.arcang);
+        c.steer = g.sum(c.steer); c.drive = g.sum(c.drive); c.probe = g.sum(c.probe);
     }
     rrt_finish<G>(a, q, g, Q, K, iters, n, sol, status, nlos, c);
     g.sync();
