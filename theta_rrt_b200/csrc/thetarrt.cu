@@ -121,22 +121,40 @@ __global__ void __launch_bounds__(256) los_batch_kernel(const uint32_t *__restri
 
 // ===========================================================================
 // K1 nearest_batch
-//   grid = (n_slices, n_qtiles); block = 256 threads = 8 warps; each warp owns
-//   TQ queries in registers and all lanes stride the CTA's node slice with
-//   coalesced 16-byte SoA loads; per-warp shuffle min-reduction with
-//   (d2, index) lexicographic order; partials go to the workspace and
-//   nearest_final_kernel folds the slices (ascending slice = ascending index).
+//   A CTA has 8 warps.  A warp owns one query set (TQ queries in registers) and one node slice; its lanes
+//   stride the slice with 16-byte SoA loads (512 B per warp per array and load), four loads of x and four of y
+//   in flight per lane.  With >= 8 query sets the warps of a CTA hold different sets and stream the same slice
+//   (reuse through L1); with fewer sets the spare warps split the CTA's slice, so that a single query still puts
+//   every warp of the GPU on the HBM stream.  Per-warp shuffle min-reduction ordered by (d2, index); partials go
+//   to the workspace and nearest_final_kernel folds them (one warp per query).
 //   d2 = rn(rn(dx*dx) + rn(dy*dy)), dx = qx - x  (search.py:15 before the sqrt).
 // ===========================================================================
 #define NN_WARPS 8
 template <int TQ>
+__device__ __forceinline__ void nn_fold(const double (&qx)[TQ], const double (&qy)[TQ], double (&bd)[TQ], int (&bi)[TQ], double2 xv, double2 yv,
+                                        int i0) {
+#pragma unroll
+    for (int t = 0; t < TQ; t++) {
+        double dx = qx[t] - xv.x, dy = qy[t] - yv.x;
+        double d = dx * dx + dy * dy;
+        if (d < bd[t]) { bd[t] = d; bi[t] = i0; }
+        dx = qx[t] - xv.y; dy = qy[t] - yv.y;
+        d = dx * dx + dy * dy;
+        if (d < bd[t]) { bd[t] = d; bi[t] = i0 + 1; }
+    }
+}
+
+template <int TQ>
 __global__ void __launch_bounds__(NN_WARPS * 32) nearest_tile_kernel(const double *__restrict__ x, const double *__restrict__ y, int64_t n_nodes,
-                                                                     const int32_t *__restrict__ qxy, int64_t n_q, int64_t slice_len,
+                                                                     const int32_t *__restrict__ qxy, int64_t n_q, int64_t slice_len, int spc_log2,
                                                                      double *__restrict__ part_d, int32_t *__restrict__ part_i) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q0 = ((int64_t)blockIdx.y * NN_WARPS + warp) * TQ;
-    if (q0 >= n_q) return;
-    const int64_t lo = (int64_t)blockIdx.x * slice_len;
+    const int spc = 1 << spc_log2, wps = NN_WARPS >> spc_log2; // query sets per CTA, warps per set
+    const int set_in_cta = warp & (spc - 1), sub = warp >> spc_log2;
+    const int64_t q0 = ((int64_t)blockIdx.x * spc + set_in_cta) * TQ;
+    const bool active = q0 < n_q;
+    const int64_t slice = (int64_t)blockIdx.y * wps + sub;
+    const int64_t lo = slice * slice_len;
     int64_t hi = lo + slice_len;
     if (hi > n_nodes) hi = n_nodes;
     double qx[TQ], qy[TQ], bd[TQ];
@@ -149,24 +167,22 @@ __global__ void __launch_bounds__(NN_WARPS * 32) nearest_tile_kernel(const doubl
         bd[t] = INFINITY;
         bi[t] = 0x7fffffff;
     }
-    // slice_len is even and x, y are 16-byte aligned (checked by the launcher): double2 loads
+    // slice_len is a multiple of 256 and x, y are 16-byte aligned (checked by the launcher): double2 loads
     const double2 *x2 = reinterpret_cast<const double2 *>(x);
     const double2 *y2 = reinterpret_cast<const double2 *>(y);
-    int64_t p = (lo >> 1) + lane, pend = hi >> 1; // pair index
-    for (; p < pend; p += 32) {
-        double2 xv = __ldg(x2 + p), yv = __ldg(y2 + p);
-        int i0 = (int)(p << 1);
-#pragma unroll
-        for (int t = 0; t < TQ; t++) {
-            double dx = qx[t] - xv.x, dy = qy[t] - yv.x;
-            double d = dx * dx + dy * dy;
-            if (d < bd[t]) { bd[t] = d; bi[t] = i0; }
-            dx = qx[t] - xv.y; dy = qy[t] - yv.y;
-            d = dx * dx + dy * dy;
-            if (d < bd[t]) { bd[t] = d; bi[t] = i0 + 1; }
-        }
+    int64_t p = (lo >> 1) + lane;
+    const int64_t pend = (active && hi > lo) ? (hi >> 1) : 0; // pair index
+    for (; p + 96 < pend; p += 128) {
+        const double2 xa = __ldg(x2 + p), xb = __ldg(x2 + p + 32), xc = __ldg(x2 + p + 64), xd = __ldg(x2 + p + 96);
+        const double2 ya = __ldg(y2 + p), yb = __ldg(y2 + p + 32), yc = __ldg(y2 + p + 64), yd = __ldg(y2 + p + 96);
+        const int i0 = (int)(p << 1);
+        nn_fold<TQ>(qx, qy, bd, bi, xa, ya, i0);
+        nn_fold<TQ>(qx, qy, bd, bi, xb, yb, i0 + 64);
+        nn_fold<TQ>(qx, qy, bd, bi, xc, yc, i0 + 128);
+        nn_fold<TQ>(qx, qy, bd, bi, xd, yd, i0 + 192);
     }
-    if ((hi & 1) && lane == 0 && hi == n_nodes) { // odd tail node of the last slice
+    for (; p < pend; p += 32) nn_fold<TQ>(qx, qy, bd, bi, __ldg(x2 + p), __ldg(y2 + p), (int)(p << 1));
+    if (active && (hi & 1) && lane == 0 && hi == n_nodes && hi > lo) { // odd tail node of the last slice
         int i0 = (int)(hi - 1);
         double xs = __ldg(x + i0), ys = __ldg(y + i0);
 #pragma unroll
@@ -176,6 +192,8 @@ __global__ void __launch_bounds__(NN_WARPS * 32) nearest_tile_kernel(const doubl
             if (d < bd[t] || (d == bd[t] && i0 < bi[t])) { bd[t] = d; bi[t] = i0; }
         }
     }
+    __shared__ double sd[NN_WARPS][TQ];
+    __shared__ int si[NN_WARPS][TQ];
 #pragma unroll
     for (int t = 0; t < TQ; t++) {
         double d = bd[t];
@@ -186,26 +204,57 @@ __global__ void __launch_bounds__(NN_WARPS * 32) nearest_tile_kernel(const doubl
             int oi = __shfl_xor_sync(0xffffffffu, i, off);
             if (od < d || (od == d && oi < i)) { d = od; i = oi; }
         }
-        if (lane == 0 && q0 + t < n_q) {
-            part_d[(int64_t)blockIdx.x * n_q + q0 + t] = d;
-            part_i[(int64_t)blockIdx.x * n_q + q0 + t] = i;
+        if (lane == 0) { sd[warp][t] = d; si[warp][t] = i; }
+    }
+    __syncthreads();
+    // the warps of one query set fold their sub-slices: one partial per (CTA column, query)
+    if (sub == 0 && active && lane < TQ && q0 + lane < n_q) {
+        double d = sd[warp][lane];
+        int i = si[warp][lane];
+        for (int w = 1; w < wps; w++) {
+            double od = sd[set_in_cta + (w << spc_log2)][lane];
+            int oi = si[set_in_cta + (w << spc_log2)][lane];
+            if (od < d || (od == d && oi < i)) { d = od; i = oi; }
         }
+        part_d[(int64_t)blockIdx.y * n_q + q0 + lane] = d;
+        part_i[(int64_t)blockIdx.y * n_q + q0 + lane] = i;
     }
 }
 
-__global__ void nearest_final_kernel(const double *__restrict__ part_d, const int32_t *__restrict__ part_i, int n_slices, int64_t n_q,
-                                     int32_t *__restrict__ idx, double *__restrict__ d2) {
-    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+// one warp per query folds the per-slice partials; (d2, index) order makes the fold order irrelevant
+__global__ void __launch_bounds__(128) nearest_final_kernel(const double *__restrict__ part_d, const int32_t *__restrict__ part_i, int n_slices,
+                                                            int64_t n_q, int32_t *__restrict__ idx, double *__restrict__ d2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (q >= n_q) return;
     double bd = INFINITY;
     int bi = 0x7fffffff;
-    for (int s = 0; s < n_slices; s++) {
+    int s = lane;
+    for (; s + 96 < n_slices; s += 128) { // four independent loads in flight
+        double d0 = part_d[(int64_t)s * n_q + q], d1 = part_d[(int64_t)(s + 32) * n_q + q];
+        double d2_ = part_d[(int64_t)(s + 64) * n_q + q], d3 = part_d[(int64_t)(s + 96) * n_q + q];
+        int i0 = part_i[(int64_t)s * n_q + q], i1 = part_i[(int64_t)(s + 32) * n_q + q];
+        int i2 = part_i[(int64_t)(s + 64) * n_q + q], i3 = part_i[(int64_t)(s + 96) * n_q + q];
+        if (d0 < bd || (d0 == bd && i0 < bi)) { bd = d0; bi = i0; }
+        if (d1 < bd || (d1 == bd && i1 < bi)) { bd = d1; bi = i1; }
+        if (d2_ < bd || (d2_ == bd && i2 < bi)) { bd = d2_; bi = i2; }
+        if (d3 < bd || (d3 == bd && i3 < bi)) { bd = d3; bi = i3; }
+    }
+    for (; s < n_slices; s += 32) {
         double d = part_d[(int64_t)s * n_q + q];
         int i = part_i[(int64_t)s * n_q + q];
         if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
     }
-    idx[q] = (bi == 0x7fffffff) ? -1 : bi;
-    if (d2) d2[q] = bd;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double od = __shfl_xor_sync(0xffffffffu, bd, off);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+        idx[q] = (bi == 0x7fffffff) ? -1 : bi;
+        if (d2) d2[q] = bd;
+    }
 }
 
 // ===========================================================================
@@ -600,29 +649,45 @@ int trrt_los_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
     return TRRT_OK;
 }
 
-// slices are even-length so that every slice starts on a 16-byte boundary
-static void nearest_plan(int64_t n_nodes, int64_t n_q, int *tq, int *n_slices, int64_t *slice_len, int *n_qtiles) {
-    int t = n_q >= 512 ? 8 : (n_q >= 128 ? 4 : (n_q >= 16 ? 2 : 1));
-    int qtiles = (int)((n_q + (int64_t)NN_WARPS * t - 1) / ((int64_t)NN_WARPS * t));
-    // aim at ~8 CTAs per SM in total, at least 4096 nodes per slice
-    int64_t want = ((int64_t)sm_count() * 8 + qtiles - 1) / qtiles;
-    int64_t max_slices = (n_nodes + 4095) / 4096;
-    if (want > max_slices) want = max_slices;
-    if (want < 1) want = 1;
-    int64_t len = (n_nodes + want - 1) / want;
-    len = (len + 63) & ~(int64_t)63;
-    if (len < 64) len = 64;
-    int slices = (int)((n_nodes + len - 1) / len);
-    if (slices < 1) slices = 1;
-    *tq = t; *n_slices = slices; *slice_len = len; *n_qtiles = qtiles;
+// Launch plan of nearest_batch: TQ queries per warp, `spc` query sets per CTA (the other 8/spc warps of a CTA split
+// its node range), grid = (node ranges, set groups).  Slices are multiples of 256 nodes (32 lanes x 2 nodes x 4 loads).
+struct NearestPlan {
+    int tq, spc_log2, grid_sets, grid_cols, n_slices;
+    int64_t slice_len;
+};
+static NearestPlan nearest_plan(int64_t n_nodes, int64_t n_q) {
+    NearestPlan P;
+    // as many queries per warp as there are (up to 8): every node load is shared by TQ queries
+    P.tq = n_q >= 8 ? 8 : (n_q > 4 ? 8 : (n_q > 2 ? 4 : (n_q > 1 ? 2 : 1)));
+    int64_t nsets = (n_q + P.tq - 1) / P.tq;
+    P.spc_log2 = 0;
+    while ((1 << P.spc_log2) < NN_WARPS && (1 << P.spc_log2) < nsets) P.spc_log2++;
+    const int spc = 1 << P.spc_log2, wps = NN_WARPS / spc;
+    P.grid_sets = (int)((nsets + spc - 1) / spc);
+    // blockIdx.x (fastest in launch order) runs over the set groups, so the CTAs that stream one node range are
+    // co-scheduled and share it through L2.  Few set groups = HBM streaming: one wave of 2 CTAs per SM.  Many set
+    // groups = fp64 bound: ~8 CTAs per SM in total so that the last wave is nearly full.
+    const int per_sm = P.grid_sets <= 2 ? 2 : 8;
+    int64_t gx = ((int64_t)sm_count() * per_sm) / P.grid_sets;
+    int64_t max_gx = (n_nodes + 2048 * (int64_t)wps - 1) / (2048 * (int64_t)wps); // at least 2048 nodes per warp slice
+    if (gx > max_gx) gx = max_gx;
+    if (gx > 65535) gx = 65535;
+    if (gx < 1) gx = 1;
+    int64_t len = (n_nodes + gx * wps - 1) / (gx * wps);
+    len = (len + 255) & ~(int64_t)255;
+    if (len < 256) len = 256;
+    int64_t slices = (n_nodes + len - 1) / len; // slices that hold nodes
+    gx = (slices + wps - 1) / wps;
+    P.grid_cols = (int)gx;
+    P.n_slices = (int)gx; // one partial per CTA column and query (the warps of a set fold their sub-slices in the CTA)
+    P.slice_len = len;
+    return P;
 }
 
 size_t trrt_nearest_workspace_bytes(int64_t n_nodes, int64_t n_q) {
     if (n_nodes <= 0 || n_q <= 0) return 16;
-    int tq, ns, nt;
-    int64_t len;
-    nearest_plan(n_nodes, n_q, &tq, &ns, &len, &nt);
-    return (size_t)ns * (size_t)n_q * (sizeof(double) + sizeof(int32_t)) + 16;
+    NearestPlan P = nearest_plan(n_nodes, n_q);
+    return (size_t)P.n_slices * (size_t)n_q * (sizeof(double) + sizeof(int32_t)) + 16;
 }
 
 int trrt_nearest_batch(const double *d_x, const double *d_y, int64_t n_nodes, const int32_t *d_qxy, int64_t n_q, int32_t *d_idx,
@@ -638,20 +703,18 @@ int trrt_nearest_batch(const double *d_x, const double *d_y, int64_t n_nodes, co
     if (!d_x || !d_y || !d_work) return TRRT_ERR_INVALID_ARGUMENT;
     if (((uintptr_t)d_x & 15) || ((uintptr_t)d_y & 15) || ((uintptr_t)d_work & 7)) return TRRT_ERR_INVALID_ARGUMENT;
     if (work_bytes < trrt_nearest_workspace_bytes(n_nodes, n_q)) return TRRT_ERR_WORKSPACE_TOO_SMALL;
-    int tq, ns, nt;
-    int64_t len;
-    nearest_plan(n_nodes, n_q, &tq, &ns, &len, &nt);
+    const NearestPlan P = nearest_plan(n_nodes, n_q);
     double *part_d = (double *)d_work;
-    int32_t *part_i = (int32_t *)(part_d + (size_t)ns * n_q);
-    dim3 grid((unsigned)ns, (unsigned)nt);
-    switch (tq) {
-    case 8: nearest_tile_kernel<8><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, len, part_d, part_i); break;
-    case 4: nearest_tile_kernel<4><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, len, part_d, part_i); break;
-    case 2: nearest_tile_kernel<2><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, len, part_d, part_i); break;
-    default: nearest_tile_kernel<1><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, len, part_d, part_i); break;
+    int32_t *part_i = (int32_t *)(part_d + (size_t)P.n_slices * n_q);
+    dim3 grid((unsigned)P.grid_sets, (unsigned)P.grid_cols);
+    switch (P.tq) {
+    case 8: nearest_tile_kernel<8><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i); break;
+    case 4: nearest_tile_kernel<4><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i); break;
+    case 2: nearest_tile_kernel<2><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i); break;
+    default: nearest_tile_kernel<1><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i); break;
     }
     CUDA_TRY(cudaGetLastError());
-    nearest_final_kernel<<<(unsigned)((n_q + 127) / 128), 128, 0, st>>>(part_d, part_i, ns, n_q, d_idx, d_d2);
+    nearest_final_kernel<<<(unsigned)((n_q * 32 + 127) / 128), 128, 0, st>>>(part_d, part_i, P.n_slices, n_q, d_idx, d_d2);
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }
