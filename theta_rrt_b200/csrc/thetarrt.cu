@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/thetarrt.h"
@@ -774,7 +775,7 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
     d.next_query = (unsigned long long *)A.d_work;
     d.tab = (int32_t *)((char *)A.d_work + 256); d.tsize = rrt_tsize(A.K);
     cudaStream_t st = (cudaStream_t)stream;
-    const int threads = 128;
+    int threads = 128;
     int64_t blocks = (A.n_queries * G + threads - 1) / threads;
     if (A.schedule == 1) { // cooperative: G lanes on one iteration at a time
         switch (G) {
@@ -788,6 +789,8 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         }
     } else if (A.schedule == 0) { // speculative window of G iterations, persistent groups
         const size_t smem = 0;
+        threads = TRRT_SPEC_THREADS;
+        blocks = (A.n_queries * G + threads - 1) / threads;
         CUDA_TRY(cudaMemsetAsync(d.next_query, 0, sizeof(unsigned long long), st));
         const void *fn = nullptr;
         switch (G) {
@@ -802,6 +805,10 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
         if (per_sm < 1) per_sm = 1;
+        if (const char *cap = getenv("TRRT_MAX_BLOCKS_PER_SM")) { // experiments only
+            int c = atoi(cap);
+            if (c >= 1 && c < per_sm) per_sm = c;
+        }
         int64_t resident = (int64_t)sm_count() * per_sm; // one full wave; groups loop over the queries
         if (blocks > resident) blocks = resident;
         RrtDev *dp = &d;

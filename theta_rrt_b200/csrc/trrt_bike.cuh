@@ -389,7 +389,7 @@ __device__ __noinline__ bool arc_literal_ge0(ArcTest &A, double vx, double vy, i
 }
 
 // does getArc keep circle pixel (px, py)?  search.py:161-181
-__device__ __forceinline__ bool arc_keeps_pixel(ArcTest &A, double bx, double by, double lx, double ly, long long px, long long py) {
+__device__ __noinline__ bool arc_keeps_pixel(ArcTest &A, double bx, double by, double lx, double ly, long long px, long long py) {
     if (!A.ready) { // lazily: only needed once a blocked circle pixel is met
         A.u1x = bx - A.iccx; A.u1y = by - A.iccy;
         A.u2x = lx - A.iccx; A.u2y = ly - A.iccy;

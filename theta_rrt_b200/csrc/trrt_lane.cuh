@@ -11,7 +11,7 @@
 namespace trrt {
 
 // search.lineofsight (search.py:35-94) by one lane.  pixels (optional) += max(|dx|,|dy|)+1 for in-bounds rays.
-__device__ __forceinline__ bool los_lane(const Grid &m, long long ax, long long ay, long long bx, long long by, int *pixels) {
+__device__ __noinline__ bool los_lane(const Grid &m, long long ax, long long ay, long long bx, long long by, int *pixels) {
     if (!m.inb(ax, ay) || !m.inb(bx, by)) return false;
     int x0 = (int)ax, y0 = (int)ay, x1 = (int)bx, y1 = (int)by;
     const int adx = abs(x1 - x0), ady = abs(y1 - y0);

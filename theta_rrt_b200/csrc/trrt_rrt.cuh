@@ -63,7 +63,7 @@ __device__ __forceinline__ unsigned hash3(double x, double y, double t) {
 }
 
 // index of the tree node equal (by value) to (x, y, t), or -1   [rrt.py:151, :179]
-__device__ __forceinline__ int tree_find(const int32_t *tab, int tmask, const double *nx, const double *ny, const double *nth, double x,
+__device__ __noinline__ int tree_find(const int32_t *tab, int tmask, const double *nx, const double *ny, const double *nth, double x,
                                          double y, double t, unsigned long long &probes) {
     unsigned s = hash3(x, y, t) & (unsigned)tmask;
     for (;;) {
@@ -75,7 +75,7 @@ __device__ __forceinline__ int tree_find(const int32_t *tab, int tmask, const do
         s = (s + 1) & (unsigned)tmask;
     }
 }
-__device__ __forceinline__ void tree_insert(int32_t *tab, int tmask, double x, double y, double t, int idx) {
+__device__ __noinline__ void tree_insert(int32_t *tab, int tmask, double x, double y, double t, int idx) {
     unsigned s = hash3(x, y, t) & (unsigned)tmask;
     while (tab[s] != 0) s = (s + 1) & (unsigned)tmask;
     tab[s] = idx + 1;
@@ -367,6 +367,9 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
 #define TRRT_SPEC_MIN_BLOCKS 4
 #endif
 
+#ifndef TRRT_SCAN_AHEAD
+#define TRRT_SCAN_AHEAD 1024
+#endif
 // private fp64 nearest scan over nodes [0, n): every lane of the warp reads the same node (broadcast loads)
 __device__ __forceinline__ void nearest_private(const double *__restrict__ nx, const double *__restrict__ ny, int n, double qx, double qy,
                                                 double &bd_out, int &bi_out) {
@@ -381,6 +384,11 @@ __device__ __forceinline__ void nearest_private(const double *__restrict__ nx, c
         const int pairs = (n - i) >> 1;
         int p = 0;
         for (; p + 1 < pairs; p += 2) {
+            // the tree streams from L2 / HBM: ask for the lines TRRT_SCAN_AHEAD bytes ahead (one request per 128-byte line)
+            if ((p & 7) == 0) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(x2 + p + TRRT_SCAN_AHEAD / 16));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(y2 + p + TRRT_SCAN_AHEAD / 16));
+            }
             const double2 xa = x2[p], ya = y2[p], xb = x2[p + 1], yb = y2[p + 1];
             const int b = i + 2 * p;
             TRRT_NODE(xa.x, ya.x, b); TRRT_NODE(xa.y, ya.y, b + 1); TRRT_NODE(xb.x, yb.x, b + 2); TRRT_NODE(xb.y, yb.y, b + 3);
@@ -397,55 +405,90 @@ __device__ __forceinline__ void nearest_private(const double *__restrict__ nx, c
     bd_out = bd; bi_out = bi;
 }
 
+// Lockstep: the expansion code (steer, libm, rays, raster: ~40 KB of SASS) is far larger than an SM's instruction
+// cache, and with warps spread over it the instruction fetches of a GPC saturate its shared cache (ncu: gcc
+// instruction requests at 85% of peak, SM i-cache hit rate 68%, half of all stall samples "no instruction").
+// So the warps of a CTA enter the expansion together: one CTA barrier per window, placed after the (tiny-code)
+// nearest scan; the first warp through a code line fetches it for the others (SM i-cache hit rate 89%, gcc at 47%).
+// A CTA is TRRT_SPEC_THREADS wide.
+#ifndef TRRT_SPEC_LOCKSTEP
+#define TRRT_SPEC_LOCKSTEP 1
+#endif
+#ifndef TRRT_SPEC_THREADS
+#define TRRT_SPEC_THREADS 256 /* measured on B200 (cfg 3): 256 x 3 lockstep 75.9 ms, 128 x 4 free-running 81.5 ms, 512 x 1 lockstep 83.6 ms */
+#endif
+#ifndef TRRT_SPEC_BLOCKS_PER_SM
+#define TRRT_SPEC_BLOCKS_PER_SM 3
+#endif
+
 template <int G>
-__global__ void __launch_bounds__(128, TRRT_SPEC_MIN_BLOCKS) rrt_kernel_spec(const RrtDev a) {
+__global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rrt_kernel_spec(const RrtDev a) {
     const Group<G> g;
     const Group<1> solo;
     const int K = a.K;
     // persistent groups: queries differ a lot in length (27% of the cfg-3 queries end early), so each group
-    // pulls the next query from a counter instead of owning a fixed one
-    for (;;) {
-    unsigned long long qq = 0;
-    if (g.gl == 0) qq = atomicAdd(a.next_query, 1ull);
-    qq = g.bcast(qq, 0);
-    if (qq >= (unsigned long long)a.nq) break;
-    const int64_t q = (int64_t)qq;
+    // pulls the next query from a counter instead of owning a fixed one.  One loop trip = one window.
+    bool have = false, drained = false;
+    int64_t q = 0;
     RrtQuery Q;
-    rrt_setup<G>(a, q, g, Q);
     RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0}; // scan is kept uniform; the others are lane-private sums, folded at the end
-    int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND;
-    int iters = 0;
-    bool running = true;
-    for (int k0 = 0; k0 < K - 1 && running; k0 += G) {
+    int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND, iters = 0, k0 = 0;
+    for (;;) {
+        if (!have && !drained) {
+            unsigned long long qq = 0;
+            if (g.gl == 0) qq = atomicAdd(a.next_query, 1ull);
+            qq = g.bcast(qq, 0);
+            if (qq >= (unsigned long long)a.nq) drained = true;
+            else {
+                q = (int64_t)qq;
+                rrt_setup<G>(a, q, g, Q);
+                c = RrtCounters{0, 0, 0, 0, 0, 0, 0, 0};
+                n = 1; nlos = 0; sol = -1; status = TRRT_OK_NOT_FOUND; iters = 0; k0 = 0;
+                have = true;
+            }
+        }
+        // ---------------- phase A, part 1: sample, `qrand in G`, nearest scan
         const int n0 = n;
-        // ---------------- phase A
-        const int my_it = k0 + g.gl;
-        int pre = -1;          // TRRT_IT_QRAND_BLOCKED, TRRT_IT_NOT_RUN (beyond the last iteration) or -1 = live
-        bool q_in_tree = false; // rrt.py:151 against the snapshot (+ nodes of this window, folded in below)
+        int pre = TRRT_IT_NOT_RUN; // TRRT_IT_QRAND_BLOCKED, TRRT_IT_NOT_RUN (beyond the last iteration / no query) or -1 = live
+        bool q_in_tree = false;    // rrt.py:151 against the snapshot (+ nodes of this window, folded in below)
         int near = -1, exist = -1; // nearest node; index of a tree node equal to qnew, or -1
         double bd = INFINITY, qx = 0, qy = 0, qth = 0;
-        double wbest = INFINITY; // squared distance to the nearest node inserted earlier in this window
+        double wbest = INFINITY;   // squared distance to the nearest node inserted earlier in this window
         int widx = -1;
         unsigned long long probes = 0;
         Expand e;
         e.code = TRRT_IT_NOT_RUN; e.flags = 0; e.lospx = e.arcpx = e.arcang = e.drive = 0;
         e.wx = e.wy = e.wth = NAN; // never equal to a node
-        if (my_it < K - 1) {
-            const int sx = __ldg(Q.sxy + 2 * my_it), sy = __ldg(Q.sxy + 2 * my_it + 1);
-            qx = (double)sx; qy = (double)sy;
-            qth = standardangle(__ldg(Q.sth + my_it));
-            if (!Q.m.freespace(sx, sy)) pre = TRRT_IT_QRAND_BLOCKED; // rrt.py:148
-            else q_in_tree = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, qx, qy, qth, probes) >= 0;
-        } else pre = TRRT_IT_NOT_RUN;
+        if (have) {
+            const int my_it = k0 + g.gl;
+            if (my_it < K - 1) {
+                const int sx = __ldg(Q.sxy + 2 * my_it), sy = __ldg(Q.sxy + 2 * my_it + 1);
+                qx = (double)sx; qy = (double)sy;
+                qth = standardangle(__ldg(Q.sth + my_it));
+                if (!Q.m.freespace(sx, sy)) pre = TRRT_IT_QRAND_BLOCKED; // rrt.py:148
+                else { pre = -1; q_in_tree = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, qx, qy, qth, probes) >= 0; }
+            }
+        }
         const bool live = (pre == -1) && !q_in_tree;
-        // the scan is executed by the whole warp (lanes without a live sample idle through it)
-        nearest_private(Q.nx, Q.ny, live ? n0 : 0, qx, qy, bd, near);
+        if (have) {
+            // the scan is executed by the whole warp (lanes without a live sample idle through it)
+            nearest_private(Q.nx, Q.ny, live ? n0 : 0, qx, qy, bd, near);
+        }
+#if TRRT_SPEC_LOCKSTEP
+        // ---------------- CTA barrier: expansion code is entered together; also the exit test
+        if (!__syncthreads_or(have ? 1 : 0)) break;
+        if (!have) continue;
+#else
+        if (!have) break; // no query left for this group
+#endif
+        // ---------------- phase A, part 2: everything after the nearest node
         if (live) {
             expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
             if (e.code == EX_ACCEPT) exist = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes);
         }
         g.sync();
         // ---------------- phase B: commit in iteration order
+        bool running = true;
         for (int j = 0; j < G; j++) {
             const int it = k0 + j;
             const int pre_j = g.bcast(pre, j);
@@ -537,15 +580,17 @@ __global__ void __launch_bounds__(128, TRRT_SPEC_MIN_BLOCKS) rrt_kernel_spec(con
         }
         c.probe += probes;
         g.sync(); // tree and index writes of this window are visible to every lane's next phase A
+        k0 += G;
+        if (!running || k0 >= K - 1) { // query finished
+            if (a.counters) { // fold the lane-private counters
+                c.los = g.sum(c.los); c.lospx = g.sum(c.lospx); c.arcpx = g.sum(c.arcpx); c.arcang = g.sum(c.arcang);
+                c.steer = g.sum(c.steer); c.drive = g.sum(c.drive); c.probe = g.sum(c.probe);
+            }
+            rrt_finish<G>(a, q, g, Q, K, iters, n, sol, status, nlos, c);
+            g.sync();
+            have = false;
+        }
     }
-    // fold the lane-private counters
-    if (a.counters) {
-        c.los = g.sum(c.los); c.lospx = g.sum(c.lospx); c.arcpx = g.sum(c.arcpx); c.arcang = g.sum(c.arcang);
-        c.steer = g.sum(c.steer); c.drive = g.sum(c.drive); c.probe = g.sum(c.probe);
-    }
-    rrt_finish<G>(a, q, g, Q, K, iters, n, sol, status, nlos, c);
-    g.sync();
-    } // next query
 }
 
 } // namespace trrt
