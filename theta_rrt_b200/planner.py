@@ -154,7 +154,7 @@ class Planner:
 
     # ------------------------------------------------------------------ K2
     def rrt(self, starts, goals, sample_xy, sample_th, K=None, params=None, map_id=None, logs=False, want_u=True,
-            counters=False, lanes=0, schedule=0):
+            counters=False, lanes=0, schedule=0, work_key="rrt", reuse=None):
         """rrt.rrt for a batch.  starts/goals float64 [q,3] (x, y, theta_deg); sample_xy int32 [q,K-1,2];
         sample_th float64 [q,K-1].  K = builtins.K (node capacity; K-1 iterations)."""
         P = params or self.params
@@ -173,22 +173,28 @@ class Planner:
             dev = self.device
             f64 = dict(dtype=torch.float64, device=dev)
             i32 = dict(dtype=torch.int32, device=dev)
-            res = RrtResult(K=K, node_x=torch.empty((nq, K), **f64), node_y=torch.empty((nq, K), **f64),
-                            node_theta=torch.empty((nq, K), **f64), parent=torch.empty((nq, K), **i32),
-                            n_nodes=torch.empty(nq, **i32), sol=torch.empty(nq, **i32), status=torch.empty(nq, **i32),
-                            iters=torch.empty(nq, **i32))
-            if want_u:
-                res.u = torch.empty((nq, K, 5), **f64)
-            if logs:
-                res.it_near = torch.empty((nq, K - 1), **i32)
-                res.it_new = torch.empty((nq, K - 1), **i32)
-                res.it_code = torch.empty((nq, K - 1), dtype=torch.uint8, device=dev)
-                res.los_log = torch.zeros((nq, 2 * (K - 1)), dtype=torch.uint8, device=dev)
-                res.n_los = torch.empty(nq, **i32)
-            if counters:
-                res.counters = torch.zeros((nq, 8), dtype=torch.int64, device=dev)
+            if reuse is not None and reuse.K == K and reuse.node_x.shape[0] == nq and (reuse.u is not None) == bool(want_u) \
+                    and (reuse.it_near is not None) == bool(logs) and (reuse.counters is not None) == bool(counters):
+                res = reuse  # caller-provided result buffers of the right shape (rrt_host keeps one set per stream)
+                if counters:
+                    res.counters.zero_()
+            else:
+                res = RrtResult(K=K, node_x=torch.empty((nq, K), **f64), node_y=torch.empty((nq, K), **f64),
+                                node_theta=torch.empty((nq, K), **f64), parent=torch.empty((nq, K), **i32),
+                                n_nodes=torch.empty(nq, **i32), sol=torch.empty(nq, **i32), status=torch.empty(nq, **i32),
+                                iters=torch.empty(nq, **i32))
+                if want_u:
+                    res.u = torch.empty((nq, K, 5), **f64)
+                if logs:
+                    res.it_near = torch.empty((nq, K - 1), **i32)
+                    res.it_new = torch.empty((nq, K - 1), **i32)
+                    res.it_code = torch.empty((nq, K - 1), dtype=torch.uint8, device=dev)
+                    res.los_log = torch.zeros((nq, 2 * (K - 1)), dtype=torch.uint8, device=dev)
+                    res.n_los = torch.empty(nq, **i32)
+                if counters:
+                    res.counters = torch.zeros((nq, 8), dtype=torch.int64, device=dev)
             wb = self.lib.trrt_rrt_workspace_bytes(nq, K)
-            work = self._scratch("rrt", wb)
+            work = self._scratch(work_key, wb)  # concurrent launches (rrt_host) must not share a workspace
             g = self.grid
             ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
             a = _lib.CRrtArgs(d_bits=g.bits.data_ptr(), n_maps=g.n_maps, H=g.H, W=g.W, d_map_id=ptr(mid),
@@ -206,6 +212,50 @@ class Planner:
             # keep inputs alive until the stream has consumed them
             res._keep = (starts, goals, sample_xy, sample_th, mid)
         return res
+
+    def rrt_host(self, starts, goals, sample_xy, sample_th, out, K=None, chunks=4, **kw):
+        """rrt.rrt for a batch whose inputs and outputs live in (pinned) HOST memory: the queries are cut into
+        `chunks` contiguous pieces, each on its own stream (host->device copy, fused kernel, device->host copy), so
+        that the PCIe transfers of one piece overlap the planning of the others.  `out` maps RrtResult field names
+        (node_x, node_y, node_theta, parent, u, n_nodes, sol, status, iters, ...) to host tensors with a leading
+        query dimension; they are filled in place.  The call returns after enqueuing; the planner's current stream
+        waits for every piece (synchronise it before reading `out`)."""
+        ins = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))
+               for t in (starts, goals, sample_xy, sample_th)]
+        nq = ins[0].shape[0]
+        chunks = max(1, min(int(chunks), nq))
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            if not hasattr(self, "_streams") or len(self._streams) < chunks:
+                self._streams = [torch.cuda.Stream(self.device) for _ in range(chunks)]
+            start = torch.cuda.Event()
+            start.record(main)
+            keep = []
+            for c in range(chunks):
+                lo, hi = nq * c // chunks, nq * (c + 1) // chunks
+                st = self._streams[c]
+                st.wait_event(start)
+                with torch.cuda.stream(st):
+                    # device buffers of a piece are allocated once and reused by later calls of the same shape
+                    key = (c, chunks, tuple((tuple(t[lo:hi].shape), t.dtype) for t in ins))
+                    cached = self._host_cache.get(key) if hasattr(self, "_host_cache") else None
+                    if cached is None:
+                        if not hasattr(self, "_host_cache"):
+                            self._host_cache = {}
+                        cached = ([torch.empty(t[lo:hi].shape, dtype=t.dtype, device=self.device) for t in ins], None)
+                    din, prev = cached
+                    for d, t in zip(din, ins):
+                        d.copy_(t[lo:hi], non_blocking=True)
+                    res = self.rrt(*din, K=K, work_key=("rrt", c), reuse=prev, **kw)
+                    self._host_cache[key] = (din, res)
+                    for name, t in out.items():
+                        t[lo:hi].copy_(getattr(res, name), non_blocking=True)
+                    keep.append((din, res))
+                done = torch.cuda.Event()
+                done.record(st)
+                main.wait_event(done)
+            self._inflight = keep  # tensors stay referenced until the next call
+        return out
 
     def findnearest(self, res: RrtResult, goals, params=None):
         """rrt.findnearest (rrt.py:117-128) for every query of an RrtResult produced with logs=True."""
