@@ -49,6 +49,13 @@ def main():
         for _ in range(2):
             p.los(seg)
         torch.cuda.synchronize()
+    elif what == "theta1":
+        p = Planner(OccupancyGrid(maps["map2"], device=dev))
+        one = torch.tensor([[280, 0, 8, 280]], dtype=torch.int32, device=dev)
+        for _ in range(2):
+            r = p.theta(one, lanes=32)
+        torch.cuda.synchronize()
+        print("theta1 done", int(r.expanded.sum()))
     elif what == "theta":
         m2 = maps["map2"]
         p = Planner(OccupancyGrid(m2, device=dev))

@@ -337,3 +337,47 @@ def test_findnearest_vs_oracle(O, maps):
         assert best[q] == b, q
         if b >= 0:
             assert abs(dist[q] - d) <= 1e-12 * max(1.0, abs(d)), q
+
+
+def test_cfg5_mixed_maps_rrt_and_theta(O):
+    """BASELINE cfg 5 in small: RRT and Theta* queries over several random synthetic 256x256 maps (4x4-block
+    Bernoulli obstacles, p = 0.15), each query bound to its map through map_id -- bitwise vs the oracle."""
+    from theta_rrt_b200 import OccupancyGrid, Params, Planner, samples
+    from oracle.c_oracle import Params as OP
+    n_maps, side = 3, 256
+    free = np.stack([util.synthetic_map(side, 0.15, 4, 7 + m) for m in range(n_maps)])
+    p = Planner(OccupancyGrid(free), Params(tol_xy=0.0))
+    rng = np.random.default_rng(55)
+    nq, K = 18, 401
+    mid = rng.integers(0, n_maps, nq).astype(np.int32)
+    starts = np.empty((nq, 3)); goals = np.empty((nq, 3))
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        s, g = util.random_queries(free[mid[q]], 1, 1000 + q)
+        starts[q], goals[q] = s[0], g[0]
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, 2000 + q, (side, side))
+    for lanes, schedule in ((32, 0), (8, 1)):
+        res = p.rrt(starts, goals, sxy, sth, K=K, logs=True, map_id=mid, lanes=lanes, schedule=schedule).host()
+        for q in range(nq):
+            o = O.rrt(free[mid[q]], ((starts[q, 0], starts[q, 1]), starts[q, 2]), ((goals[q, 0], goals[q, 1]), goals[q, 2]),
+                      sxy[q], sth[q], OP(tol_xy=0.0), K=K)
+            n = o["n_nodes"]
+            assert int(res["n_nodes"][q]) == n and int(res["status"][q]) == o["status"], (q, lanes)
+            assert np.array_equal(res["parent"][q, :n], o["parent"]) and np.array_equal(res["it_near"][q], o["it_near"]), (q, lanes)
+            assert bits_equal(res["node_x"][q, :n], o["x"]) and bits_equal(res["node_theta"][q, :n], o["theta"]), (q, lanes)
+    # Theta* on the same maps (unreachable goals allowed -> status)
+    nt = 60
+    tm = rng.integers(0, n_maps, nt).astype(np.int32)
+    sg = np.empty((nt, 4), np.int32)
+    for q in range(nt):
+        cells = np.argwhere(free[tm[q]])
+        a, b = cells[rng.integers(len(cells), size=2)]
+        sg[q] = (a[1], a[0], b[1], b[0])
+    r = p.theta(sg, map_id=tm, path_cap=4096).host()
+    for q in range(nt):
+        o = O.astar(free[tm[q]], sg[q, :2], sg[q, 2:], log_los=False)
+        assert int(r["status"][q]) == o["status"], q
+        if o["status"] == 0:
+            n = int(r["path_len"][q])
+            assert [tuple(v) for v in r["path"][q, :n].tolist()] == o["path"] and r["cost"][q] == o["cost"], q
+            assert int(r["expanded"][q]) == o["expanded"] and int(r["n_los"][q]) == o["n_los"], q

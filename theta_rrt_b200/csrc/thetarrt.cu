@@ -370,40 +370,90 @@ struct ThetaDev {
 
 __device__ __forceinline__ bool hless(double f1, unsigned c1, double f2, unsigned c2) { return f1 < f2 || (f1 == f2 && c1 < c2); }
 
-__device__ __forceinline__ bool heap_push(HeapEnt *h, int &size, int cap, double f, unsigned c) {
+// The open list is a G-ary heap (G = lanes of the group): node i has children G*i+1 .. G*i+G.  A pop descends
+// log_G(size) levels (3 for the 2 800 entries of the map2 query with G = 32) and at each level the G children are
+// read with one coalesced load and reduced with shuffles, instead of the ~12 dependent compare-and-swap rounds one
+// lane would spend in a binary heap.  Pushes climb at most the same levels (leader only).  The top three levels
+// (1 + G + G*G entries, 12.7 KB per query for G = 32) live in SHARED memory as SoA (f[], cell[]); deeper levels spill
+// to the global workspace.  Level boundaries coincide with the shared/global boundary, so one level of children is
+// entirely on one side.  Any correct min-heap on the total order (f, cell) pops in the reference's PriorityQueue
+// order (search.py:231,249).
+#ifndef TRRT_THETA_SMEM_HEAP
+#define TRRT_THETA_SMEM_HEAP 0 /* measured on B200: L1-resident global heap 241 ms vs shared top levels 292 ms (2048 map2 queries) */
+#endif
+template <int G>
+struct Heap {
+    static constexpr int SCAP = TRRT_THETA_SMEM_HEAP ? 1 + G + G * G : 0;
+    double *sf;    // shared
+    unsigned *sc;  // shared
+    HeapEnt *gh;   // global, indexed by heap position (the first SCAP slots are unused)
+    __device__ __forceinline__ void get(int i, double &f, unsigned &c) const {
+        if (SCAP > 0 && i < SCAP) { f = sf[i]; c = sc[i]; }
+        else { HeapEnt e = gh[i]; f = e.f; c = e.c; }
+    }
+    __device__ __forceinline__ void put(int i, double f, unsigned c) const {
+        if (SCAP > 0 && i < SCAP) { sf[i] = f; sc[i] = c; }
+        else { HeapEnt e; e.f = f; e.c = c; e.pad = 0; gh[i] = e; }
+    }
+};
+
+template <int G>
+__device__ __forceinline__ bool heap_push(const Heap<G> &h, int &size, int cap, double f, unsigned c) {
     if (size >= cap) return false;
     int i = size++;
     while (i > 0) {
-        int p = (i - 1) >> 1;
-        HeapEnt e = h[p];
-        if (!hless(f, c, e.f, e.c)) break;
-        h[i] = e;
+        const int p = (i - 1) / G;
+        double pf;
+        unsigned pc;
+        h.get(p, pf, pc);
+        if (!hless(f, c, pf, pc)) break;
+        h.put(i, pf, pc);
         i = p;
     }
-    HeapEnt n;
-    n.f = f; n.c = c; n.pad = 0;
-    h[i] = n;
+    h.put(i, f, c);
     return true;
 }
-__device__ __forceinline__ HeapEnt heap_pop(HeapEnt *h, int &size) {
-    HeapEnt top = h[0];
-    HeapEnt last = h[--size];
+// cooperative pop: every lane of the group calls it with the same arguments and receives the same result.
+// f >= 0 always (sums of distances), so the IEEE bit pattern of f orders like f and the group minimum of
+// (f, cell) is three 32-bit warp reductions (REDUX) -- high word, low word, cell -- each over the lanes still tied.
+template <int G>
+__device__ __forceinline__ void heap_pop(const Group<G> &g, const Heap<G> &h, int &size, double &top_f, unsigned &top_c) {
+    h.get(0, top_f, top_c);
+    double lf;
+    unsigned lc;
+    h.get(--size, lf, lc);
+    const int base = (threadIdx.x & 31) & ~(G - 1);
     int i = 0;
     for (;;) {
-        int c = 2 * i + 1;
-        if (c >= size) break;
-        HeapEnt a = h[c];
-        if (c + 1 < size) {
-            HeapEnt b = h[c + 1];
-            if (hless(b.f, b.c, a.f, a.c)) { a = b; c++; }
-        }
-        if (!hless(a.f, a.c, last.f, last.c)) break;
-        h[i] = a;
-        i = c;
+        const int fc = G * i + 1;
+        if (fc >= size) break;
+        double bf = INFINITY;
+        unsigned bc = 0xffffffffu;
+        if (fc + g.gl < size) h.get(fc + g.gl, bf, bc);
+        const unsigned long long kb = (unsigned long long)__double_as_longlong(bf);
+        const unsigned hi = (unsigned)(kb >> 32), lo = (unsigned)kb;
+        const unsigned mh = __reduce_min_sync(g.mask, hi);
+        bool cand = hi == mh;
+        const unsigned ml = __reduce_min_sync(g.mask, cand ? lo : 0xffffffffu);
+        cand = cand && lo == ml;
+        const unsigned mc = __reduce_min_sync(g.mask, cand ? bc : 0xffffffffu);
+        cand = cand && bc == mc;
+        const int bl = __ffs(__ballot_sync(g.mask, cand) & g.mask) - 1 - base; // equal keys are interchangeable
+        const double mf = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+        if (!hless(mf, mc, lf, lc)) break;
+        if (g.gl == 0) h.put(i, mf, mc);
+        i = fc + bl;
     }
-    if (size > 0) h[i] = last;
-    return top;
+    g.sync(); // children were read by all lanes before the leader overwrites a slot on the path
+    if (size > 0 && g.gl == 0) h.put(i, lf, lc);
+    g.sync();
 }
+
+// Cells are named by pk = (x << 16) | y: the same order as the reference's (x, y) tuples, no division to get the
+// coordinates back, and x*W + y is one multiply-add when the per-cell record is needed.
+__device__ __forceinline__ unsigned pk_of(int x, int y) { return ((unsigned)x << 16) | (unsigned)y; }
+__device__ __forceinline__ int pk_x(unsigned pk) { return (int)(pk >> 16); }
+__device__ __forceinline__ int pk_y(unsigned pk) { return (int)(pk & 0xffffu); }
 
 template <int G>
 __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
@@ -414,7 +464,16 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
     const bool lead = g.gl == 0;
     const int W = a.W, H = a.H;
     Cell *cells = a.cells + (size_t)slot * H * W;
-    HeapEnt *heap = a.heap + (size_t)slot * a.heap_cap;
+    extern __shared__ __align__(16) unsigned char theta_smem[];
+    Heap<G> heap;
+    {
+        constexpr int groups = 128 / G, SC = Heap<G>::SCAP;
+        const int gi = threadIdx.x / G;
+        heap.sf = reinterpret_cast<double *>(theta_smem) + gi * SC;
+        heap.sc = reinterpret_cast<unsigned *>(reinterpret_cast<double *>(theta_smem) + groups * SC) + gi * SC;
+        heap.gh = a.heap + (size_t)slot * a.heap_cap;
+    }
+    const int base_lane = (threadIdx.x & 31) & ~(G - 1);
     // neighbour j = node - delta_j, delta in itertools.product([-1,0,1], repeat=2) minus (0,0)  (search.py:187-189)
     const int j = g.gl & 7;
     const int ndx = (j < 3) ? 1 : (j < 5 ? 0 : -1);
@@ -437,9 +496,9 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
         bool overflow = false;
         if (!m.inb(sx, sy) || !m.inb(gx, gy)) status = TRRT_ERR_ENDPOINT_INVALID;                  // search.py:222
         else if (!m.free_nb(sx, sy) || !m.free_nb(gx, gy)) status = TRRT_ERR_ENDPOINT_BLOCKED;    // search.py:225
-        const unsigned goal_c = (unsigned)(gx * W + gy);
+        const unsigned goal_c = pk_of(gx, gy);
         if (status == TRRT_OK_NOT_FOUND) {
-            const unsigned sc = (unsigned)(sx * W + sy);
+            const unsigned sc = pk_of(sx, sy);
             // seed: expand the start node (search.py:237-244)
             double pf = 0;
             unsigned pc = 0;
@@ -447,34 +506,33 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
             if (g.gl < 8) {
                 int x = sx + ndx, y = sy + ndy;
                 if (m.freespace(x, y)) {
-                    unsigned c = (unsigned)(x * W + y);
                     Cell v; v.g = ndist; v.parent = (int)sc; v.stamp = (epoch << 2) | 1u;
-                    cells[c] = v;
+                    cells[x * W + y] = v;
                     double hx = (double)(gx - x), hy = (double)(gy - y);
                     pf = ndist + sqrt(hx * hx + hy * hy);
-                    pc = c; has = true;
+                    pc = pk_of(x, y); has = true;
                 }
             }
-            if (lead) { Cell v; v.g = 0.0; v.parent = -1; v.stamp = (epoch << 2) | 2u; cells[sc] = v; }
+            if (lead) { Cell v; v.g = 0.0; v.parent = -1; v.stamp = (epoch << 2) | 2u; cells[sx * W + sy] = v; }
             nclosed = 1;
             for (int t = 0; t < 8; t++) {
                 bool h1 = g.bcast(has, t); double f1 = g.bcast(pf, t); unsigned c1 = g.bcast(pc, t);
-                if (h1) { if (lead && !heap_push(heap, hsize, a.heap_cap, f1, c1)) overflow = true; npush++; }
+                if (h1) { if (lead && !heap_push<G>(heap, hsize, a.heap_cap, f1, c1)) overflow = true; npush++; }
             }
             hsize = g.bcast(hsize, 0);
             overflow = g.bcast(overflow, 0);
             g.sync();
             // main loop (search.py:247-304)
             while (hsize > 0 && !overflow) {
-                HeapEnt top;
-                if (lead) top = heap_pop(heap, hsize);
-                unsigned cur = g.bcast(top.c, 0);
-                hsize = g.bcast(hsize, 0);
-                Cell cc = cells[cur];
+                double top_f;
+                unsigned cur;
+                heap_pop<G>(g, heap, hsize, top_f, cur); // hsize stays uniform: every lane decrements its copy
+                const int cx = pk_x(cur), cy = pk_y(cur);
+                const int cur_i = cx * W + cy;
+                Cell cc = cells[cur_i];
                 if (cc.stamp & 2u) continue; // already closed: stale heap copy (search.py:250-255); epoch matches by construction
-                const int cx = (int)(cur / (unsigned)W), cy = (int)(cur % (unsigned)W);
                 if (a.thetastar) { // search.py:258-263
-                    int px = cc.parent / W, py = cc.parent % W;
+                    const int px = pk_x((unsigned)cc.parent), py = pk_y((unsigned)cc.parent);
                     bool los = los_group<G>(g, m, cx, cy, px, py);
                     if (los_log && lead && nlos < a.los_cap) los_log[nlos] = los ? 1 : 0;
                     nlos++;
@@ -485,9 +543,8 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                         if (g.gl < 8) {
                             int x = cx + ndx, y = cy + ndy;
                             if (m.freespace(x, y)) {
-                                unsigned c = (unsigned)(x * W + y);
-                                Cell nb = cells[c];
-                                if ((nb.stamp >> 2) == epoch && (nb.stamp & 2u)) { v = nb.g + ndist; vi = j; vc = c; }
+                                Cell nb = cells[x * W + y];
+                                if ((nb.stamp >> 2) == epoch && (nb.stamp & 2u)) { v = nb.g + ndist; vi = j; vc = pk_of(x, y); }
                             }
                         }
                         double bv = v;
@@ -501,20 +558,21 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                 }
                 cc.stamp = (epoch << 2) | 2u; // openSet.remove, closedSet.add (search.py:265-266)
                 g.sync(); // every lane has read cells[cur] (lanes are not in lockstep) before the leader rewrites it
-                if (lead) cells[cur] = cc;
+                if (lead) cells[cur_i] = cc;
                 nclosed++;
                 if (cur == goal_c) { status = TRRT_OK_FOUND; break; }
                 // neighbours (search.py:274-304), one lane each
                 const unsigned pcell = (unsigned)cc.parent;
-                const double gpar = a.thetastar ? cells[pcell].g : 0.0;
+                const int ppx = pk_x(pcell), ppy = pk_y(pcell);
+                const double gpar = a.thetastar ? cells[ppx * W + ppy].g : 0.0;
                 int np_ = 0;
                 double f1 = 0, f2 = 0;
                 unsigned nbc = 0;
                 if (g.gl < 8) {
                     int x = cx + ndx, y = cy + ndy;
                     if (m.freespace(x, y)) {
-                        unsigned c = (unsigned)(x * W + y);
-                        Cell nb = cells[c];
+                        const int ci = x * W + y;
+                        Cell nb = cells[ci];
                         bool mine = (nb.stamp >> 2) == epoch;
                         bool closed = mine && (nb.stamp & 2u);
                         if (!closed) {
@@ -526,7 +584,6 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                             if (!open) { nb.g = gn; nb.parent = (int)cur; nb.stamp = (epoch << 2) | 1u; f1 = gn + hh; np_ = 1; dirty = true; }
                             else if (gn < nb.g) { nb.g = gn; nb.parent = (int)cur; f1 = gn + hh; np_ = 1; dirty = true; }
                             if (a.thetastar) {
-                                int ppx = (int)(pcell / (unsigned)W), ppy = (int)(pcell % (unsigned)W);
                                 double ex = (double)(x - ppx), ey = (double)(y - ppy);
                                 double g2 = gpar + sqrt(ex * ex + ey * ey);
                                 if (g2 < nb.g) {
@@ -534,19 +591,22 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                                     if (np_ == 0) { f1 = g2 + hh; np_ = 1; } else { f2 = g2 + hh; np_ = 2; }
                                 }
                             }
-                            if (dirty) cells[c] = nb;
-                            nbc = c;
+                            if (dirty) cells[ci] = nb;
+                            nbc = pk_of(x, y);
                         }
                     }
                 }
-                for (int t = 0; t < 8; t++) {
-                    int cnt = g.bcast(np_, t);
-                    if (cnt == 0) continue;
-                    double fa = g.bcast(f1, t), fb = g.bcast(f2, t);
-                    unsigned c1 = g.bcast(nbc, t);
+                // pushes in neighbour order (search.py:279-304): only the lanes that have one
+                unsigned todo = (__ballot_sync(g.mask, np_ > 0) & g.mask) >> base_lane;
+                while (todo) {
+                    const int t = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int cnt = g.bcast(np_, t);
+                    const double fa = g.bcast(f1, t), fb = g.bcast(f2, t);
+                    const unsigned c1 = g.bcast(nbc, t);
                     if (lead) {
-                        if (!heap_push(heap, hsize, a.heap_cap, fa, c1)) overflow = true;
-                        if (cnt == 2 && !heap_push(heap, hsize, a.heap_cap, fb, c1)) overflow = true;
+                        if (!heap_push<G>(heap, hsize, a.heap_cap, fa, c1)) overflow = true;
+                        if (cnt == 2 && !heap_push<G>(heap, hsize, a.heap_cap, fb, c1)) overflow = true;
                     }
                     npush += cnt;
                 }
@@ -557,18 +617,18 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
             if (overflow) status = TRRT_ERR_CAPACITY;
         }
         g.sync();
-        // reconstruct (search.py:196-204) + cost, by the leader; the heap array is free now and serves as scratch
+        // reconstruct (search.py:196-204) + cost, by the leader; the global heap array is free now and serves as scratch
         if (lead) {
             int len = 0;
             double cost = 0.0;
             if (status == TRRT_OK_FOUND) {
                 unsigned c = goal_c;
-                unsigned *scratch = reinterpret_cast<unsigned *>(heap);
+                unsigned *scratch = reinterpret_cast<unsigned *>(heap.gh);
                 const long long scap = (long long)a.heap_cap * 4;
                 for (;;) {
                     if (len < scap) scratch[len] = c;
                     len++;
-                    int p = cells[c].parent;
+                    int p = cells[pk_x(c) * W + pk_y(c)].parent;
                     if (p < 0) break;
                     c = (unsigned)p;
                 }
@@ -578,7 +638,7 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                     int ppx = 0, ppy = 0;
                     for (int i = 0; i < len; i++) {
                         unsigned cidx = scratch[len - 1 - i];
-                        int x = (int)(cidx / (unsigned)W), y = (int)(cidx % (unsigned)W);
+                        int x = pk_x(cidx), y = pk_y(cidx);
                         if (path && i < a.path_cap) { path[2 * i] = x; path[2 * i + 1] = y; }
                         if (i > 0) { double ex = (double)(x - ppx), ey = (double)(y - ppy); cost += sqrt(ex * ex + ey * ey); }
                         ppx = x; ppy = y;
@@ -929,10 +989,15 @@ int trrt_theta_batch(const trrt_theta_args *args, void *stream) {
     CUDA_TRY(cudaMemsetAsync(w, 0, 256 + theta_cells_bytes(&A), st));
     const int threads = 128;
     int64_t blocks = ((int64_t)A.n_slots * G + threads - 1) / threads;
+    // shared memory: the top three heap levels of every group of the CTA, 12 bytes per entry
+    const size_t smem = TRRT_THETA_SMEM_HEAP ? (size_t)(threads / G) * (size_t)(1 + G + G * G) * 12 : 0;
     switch (G) {
-    case 8: theta_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(d); break;
-    case 16: theta_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(d); break;
-    default: theta_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(d); break;
+    case 8: theta_kernel<8><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+    case 16: theta_kernel<16><<<(unsigned)blocks, threads, smem, st>>>(d); break;
+    default:
+        CUDA_TRY(cudaFuncSetAttribute(theta_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        theta_kernel<32><<<(unsigned)blocks, threads, smem, st>>>(d);
+        break;
     }
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
