@@ -1,5 +1,5 @@
 set -e
-for cfg in "1024 1 1" "1024 1 0" "768 1 1" "256 3 0" "256 3 1" "128 5 0"; do set -- $cfg
+for cfg in "128 6 1" "128 5 1" "192 4 1" "384 2 1" "256 4 1"; do set -- $cfg
   python theta_rrt_b200/build.py -DTRRT_SPEC_THREADS=$1 -DTRRT_SPEC_BLOCKS_PER_SM=$2 -DTRRT_SPEC_LOCKSTEP=$3 > /dev/null 2>&1
   python bench.py --steps 3 --warmup 3 --skip-secondary --skip-cpu > gpurun_out/sw_x.json 2>gpurun_out/sw.err
   python -c "

@@ -120,6 +120,49 @@ __global__ void __launch_bounds__(256) los_batch_kernel(const uint32_t *__restri
     out[i] = ok ? 1 : 0;
 }
 
+// K4, group version: G lanes share one segment.  Lane l tests pixels l, l+G, l+2G, ... of the line; the minor-axis
+// offset of pixel i is floor((2*dmin*i + dmaj - 1) / (2*dmaj)), advanced by G pixels per step with
+// a quotient/remainder pair, so there is one division per segment, not per pixel.  Rays in a batch differ wildly in
+// length and most are blocked after a few pixels: with one thread per ray a warp runs at ~8 active lanes, with 8
+// lanes per ray the early exit frees all 8 at once.
+template <int G>
+__global__ void __launch_bounds__(256) los_group_kernel(const uint32_t *__restrict__ bits, int H, int W, int wpr, const int32_t *__restrict__ map_id,
+                                                        const int4 *__restrict__ seg, int64_t n, uint8_t *__restrict__ out) {
+    const Group<G> g;
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    if (i >= n) return; // whole groups leave together
+    const int4 s4 = __ldg(seg + i);
+    int x0 = s4.x, y0 = s4.y, x1 = s4.z, y1 = s4.w;
+    const uint32_t *gm = bits + (map_id ? (size_t)__ldg(map_id + i) * H * wpr : 0);
+    bool ok = x0 >= 0 && y0 >= 0 && x1 >= 0 && y1 >= 0 && x0 < H && x1 < H && y0 < W && y1 < W; // search.py:17-24
+    if (ok) {
+        const int adx = abs(x1 - x0), ady = abs(y1 - y0);
+        const bool low = ady < adx; // search.py:47
+        if (low ? (x0 > x1) : (y0 > y1)) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+        const unsigned dmaj = low ? adx : ady, dmin = low ? ady : adx;
+        const int step = low ? ((y1 < y0) ? -1 : 1) : ((x1 < x0) ? -1 : 1);
+        const int a0 = low ? x0 : y0, b0 = low ? y0 : x0;
+        const unsigned den = dmaj ? 2u * dmaj : 1u;
+        const unsigned num0 = 2u * dmin * (unsigned)g.gl + dmaj - (dmaj ? 1u : 0u);
+        unsigned sm = num0 / den, rem = num0 - sm * den;
+        const unsigned inc = 2u * dmin * (unsigned)G, q = inc / den, r = inc - q * den;
+        for (unsigned base = 0;; base += G) {
+            const unsigned k = base + (unsigned)g.gl;
+            bool blocked = false;
+            if (k <= dmaj) {
+                const int a = a0 + (int)k, b = b0 + step * (int)sm;
+                const int px = low ? a : b, py = low ? b : a;
+                blocked = !((__ldg(gm + (size_t)py * wpr + (px >> 5)) >> (px & 31)) & 1u);
+            }
+            if (g.any(blocked)) { ok = false; break; }
+            if (base + G > dmaj) break;
+            sm += q; rem += r;
+            if (rem >= den) { rem -= den; sm++; }
+        }
+    }
+    if (g.gl == 0) out[i] = ok ? 1 : 0;
+}
+
 // ===========================================================================
 // K1 nearest_batch
 //   A CTA has 8 warps.  A warp owns one query set (TQ queries in registers) and one node slice; its lanes
@@ -704,8 +747,22 @@ int trrt_los_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
     if (n < 0 || !d_bits || (n > 0 && (!d_seg || !d_out))) return TRRT_ERR_INVALID_ARGUMENT;
     if (n == 0) return TRRT_OK;
     if (((uintptr_t)d_seg & 15) != 0) return TRRT_ERR_INVALID_ARGUMENT;
-    int64_t blocks = (n + 255) / 256;
-    los_batch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_bits, H, W, (W + 31) / 32, d_map_id, (const int4 *)d_seg, n, d_out);
+    // lanes per segment: 1 = one thread per ray (literal Bresenham).  Measured on the cfg-4 rays (2^20 rays of 1..512 px,
+    // 88% blocked): 1 lane 232 us, 8 lanes 231 us, 16 lanes 208 us, 32 lanes 253 us; short clear rays (Theta*) favour 1.
+    int lanes = 1;
+    if (const char *e = getenv("TRRT_LOS_LANES")) lanes = atoi(e); // experiments only
+    const int wpr = (W + 31) / 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int4 *sg = (const int4 *)d_seg;
+    const unsigned blocks = (unsigned)((n * (lanes > 1 ? lanes : 1) + 255) / 256);
+    switch (lanes) {
+    case 2: los_group_kernel<2><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
+    case 4: los_group_kernel<4><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
+    case 8: los_group_kernel<8><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
+    case 16: los_group_kernel<16><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
+    case 32: los_group_kernel<32><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
+    default: los_batch_kernel<<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break; // one thread per segment
+    }
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }
@@ -730,7 +787,7 @@ static NearestPlan nearest_plan(int64_t n_nodes, int64_t n_q) {
     // groups = fp64 bound: ~8 CTAs per SM in total so that the last wave is nearly full.
     const int per_sm = P.grid_sets <= 2 ? 2 : 8;
     int64_t gx = ((int64_t)sm_count() * per_sm) / P.grid_sets;
-    int64_t max_gx = (n_nodes + 2048 * (int64_t)wps - 1) / (2048 * (int64_t)wps); // at least 2048 nodes per warp slice
+    int64_t max_gx = (n_nodes + 512 * (int64_t)wps - 1) / (512 * (int64_t)wps); // at least 512 nodes per warp slice
     if (gx > max_gx) gx = max_gx;
     if (gx > 65535) gx = 65535;
     if (gx < 1) gx = 1;

@@ -405,6 +405,67 @@ __device__ __forceinline__ void nearest_private(const double *__restrict__ nx, c
     bd_out = bd; bi_out = bi;
 }
 
+// The same scan for a full warp on one query, staged through shared memory.  In nearest_private every node costs
+// the warp two broadcast loads that each fetch 16 useful bytes and stall on L1/L2 (ncu: 45% of the kernel's
+// long-scoreboard stalls sit on those loads, and the CTA barrier then waits for the slowest scan).  Here the warp
+// copies the tree tile by tile with cp.async (LDGSTS, 512 coalesced bytes per instruction), two tiles in flight, and
+// all lanes read the tile from shared memory (conflict-free broadcast) while the next one is landing.
+#define TRRT_TILE_PAIRS 64 /* double2 pairs of x (and of y) per tile = 128 nodes; 2 tiles x 2 arrays x 1 KB per warp */
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE_PAIRS] of this warp */, const double *__restrict__ nx,
+                                               const double *__restrict__ ny, int n, double qx, double qy, double &bd_out, int &bi_out) {
+    const int lane = threadIdx.x & 31;
+    double bd = INFINITY;
+    int bi = 0x7fffffff;
+    int i = 0;
+#define TRRT_NODE(xv, yv, idx) { double dx = qx - (xv), dy = qy - (yv); double d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = (idx); } }
+    if ((((uintptr_t)nx ^ (uintptr_t)ny) & 15) == 0) { // rows equally aligned
+        if (((uintptr_t)nx & 15) != 0 && n > 0) { TRRT_NODE(nx[0], ny[0], 0); i = 1; }
+        const double2 *x2 = reinterpret_cast<const double2 *>(nx + i);
+        const double2 *y2 = reinterpret_cast<const double2 *>(ny + i);
+        const int pairs = (n - i) >> 1;
+        const int tiles = (pairs + TRRT_TILE_PAIRS - 1) / TRRT_TILE_PAIRS;
+        auto issue = [&](int t) { // lanes copy pairs lane, lane + 32 of tile t (only pairs that exist)
+            double2 *bx = tile + (t & 1) * 2 * TRRT_TILE_PAIRS, *by = bx + TRRT_TILE_PAIRS;
+            const int p0 = t * TRRT_TILE_PAIRS;
+#pragma unroll
+            for (int k = 0; k < TRRT_TILE_PAIRS / 32; k++) {
+                const int p = p0 + lane + 32 * k;
+                if (p < pairs) { cp_async16(bx + lane + 32 * k, x2 + p); cp_async16(by + lane + 32 * k, y2 + p); }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (tiles > 0) issue(0);
+        for (int t = 0; t < tiles; t++) {
+            if (t + 1 < tiles) { issue(t + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp(); // every lane's part of tile t has landed
+            const double2 *bx = tile + (t & 1) * 2 * TRRT_TILE_PAIRS, *by = bx + TRRT_TILE_PAIRS;
+            const int p0 = t * TRRT_TILE_PAIRS;
+            const int cnt = pairs - p0 < TRRT_TILE_PAIRS ? pairs - p0 : TRRT_TILE_PAIRS;
+            int p = 0;
+            for (; p + 1 < cnt; p += 2) {
+                const double2 xa = bx[p], ya = by[p], xb = bx[p + 1], yb = by[p + 1];
+                const int b = i + 2 * (p0 + p);
+                TRRT_NODE(xa.x, ya.x, b); TRRT_NODE(xa.y, ya.y, b + 1); TRRT_NODE(xb.x, yb.x, b + 2); TRRT_NODE(xb.y, yb.y, b + 3);
+            }
+            if (p < cnt) {
+                const double2 xa = bx[p], ya = by[p];
+                const int b = i + 2 * (p0 + p);
+                TRRT_NODE(xa.x, ya.x, b); TRRT_NODE(xa.y, ya.y, b + 1);
+            }
+            __syncwarp(); // tile t may be overwritten by the copy of tile t + 2
+        }
+        i += 2 * pairs;
+    }
+    for (; i < n; i++) TRRT_NODE(nx[i], ny[i], i);
+#undef TRRT_NODE
+    bd_out = bd; bi_out = bi;
+}
+
 // Lockstep: the expansion code (steer, libm, rays, raster: ~40 KB of SASS) is far larger than an SM's instruction
 // cache, and with warps spread over it the instruction fetches of a GPC saturate its shared cache (ncu: gcc
 // instruction requests at 85% of peak, SM i-cache hit rate 68%, half of all stall samples "no instruction").
@@ -426,6 +487,8 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
     const Group<G> g;
     const Group<1> solo;
     const int K = a.K;
+    __shared__ __align__(16) double2 scan_tiles[(G == 32) ? (TRRT_SPEC_THREADS / 32) * 4 * TRRT_TILE_PAIRS : 1];
+    double2 *scan_tile = scan_tiles + ((G == 32) ? (threadIdx.x >> 5) * 4 * TRRT_TILE_PAIRS : 0);
     // persistent groups: queries differ a lot in length (27% of the cfg-3 queries end early), so each group
     // pulls the next query from a counter instead of owning a fixed one.  One loop trip = one window.
     bool have = false, drained = false;
@@ -471,8 +534,9 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         }
         const bool live = (pre == -1) && !q_in_tree;
         if (have) {
-            // the scan is executed by the whole warp (lanes without a live sample idle through it)
-            nearest_private(Q.nx, Q.ny, live ? n0 : 0, qx, qy, bd, near);
+            // the scan is executed by the whole warp (lanes without a live sample run through it with a dummy point)
+            if (G == 32) nearest_staged(scan_tile, Q.nx, Q.ny, n0, qx, qy, bd, near);
+            else nearest_private(Q.nx, Q.ny, live ? n0 : 0, qx, qy, bd, near);
         }
 #if TRRT_SPEC_LOCKSTEP
         // ---------------- CTA barrier: expansion code is entered together; also the exit test
