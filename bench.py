@@ -346,7 +346,7 @@ def main():
     if dist_on:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = expansions_per_step_all * args.steps / (float(te.item()) / 1e3)
-    launches_timed += args.steps
+    launches_e2e = args.steps * args.chunks
     assert int(h_out["n_nodes"].sum()) == n_nodes_total  # the host really received this step's trees
     keep.clear()
     del h_out
@@ -366,7 +366,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "expansions/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) / args.steps,
                     "api": "Planner.rrt_host(pinned inputs, pinned outputs, chunks=%d)" % args.chunks},
-            "gpu_launches": launches_timed,
+            "gpu_launches": launches_timed, "gpu_launches_e2e": launches_e2e,
             "roofline": roofline,
             "expansions_per_step": expansions_per_step_all,
             "accepted_nodes_per_sec": (int(it_all[1].item()) - total_q) * args.steps / (total_ms_max / 1e3),
@@ -450,6 +450,19 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args):
                                                     "peak_source": peak_src,
                                                     "note": "one query, 256 MiB SoA tree (> L2): every byte comes from HBM"}}
     del xb, yb, x, y
+    if not args.skip_cpu:
+        # CPU port (oracle) on a bounded sample of the same rays, all host threads
+        from oracle import c_oracle as O
+        cores = os.cpu_count() or 1
+        O.lib()
+        ns = 1 << 17
+        O.lineofsight_batch(big, seg[:4096], threads=cores)
+        t = time.perf_counter()
+        cpu_vis = O.lineofsight_batch(big, seg[:ns], threads=cores)
+        dt = time.perf_counter() - t
+        assert np.array_equal(cpu_vis, vis[:ns])  # same booleans as the kernel
+        out["los_cfg4"]["cpu_baseline"] = {"value": ns / dt, "unit": "checks/s", "cores": cores, "kind": "port",
+                                           "sample": f"first {ns} of the {len(seg)} rays on {cores} threads"}
     # ---- Theta* on map2: the reference's single query and a batch of random free-cell queries
     m2 = maps["map2"]
     pt = Planner(OccupancyGrid(m2, device=dev))
@@ -470,6 +483,18 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args):
                                "unit": "expansions/s", "ms": msb, "queries": nqt,
                                "los_checks_per_sec": float(rb["n_los"].sum()) / (msb / 1e3),
                                "found": int((rb["status"] == 0).sum())}
+    if not args.skip_cpu:
+        from oracle import c_oracle as O
+        cores = os.cpu_count() or 1
+        nsmp = min(nqt, 4 * cores)
+        sgh = sg[:nsmp].cpu().numpy()
+        t = time.perf_counter()
+        rc = O.astar_batch(m2, sgh, thetastar=True, threads=cores)
+        dt = time.perf_counter() - t
+        assert np.array_equal(rc["expanded"], rb["expanded"][:nsmp])  # same searches as the kernel
+        out["theta_batch_map2"]["cpu_baseline"] = {"value": float(rc["expanded"].sum()) / dt, "unit": "expansions/s",
+                                                   "cores": cores, "kind": "port",
+                                                   "sample": f"first {nsmp} of the {nqt} queries on {cores} threads"}
     return out
 
 

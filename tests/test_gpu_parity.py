@@ -381,3 +381,62 @@ def test_cfg5_mixed_maps_rrt_and_theta(O):
             n = int(r["path_len"][q])
             assert [tuple(v) for v in r["path"][q, :n].tolist()] == o["path"] and r["cost"][q] == o["cost"], q
             assert int(r["expanded"][q]) == o["expanded"] and int(r["n_los"][q]) == o["n_los"], q
+
+
+def test_rrt_edge_cases(O, maps):
+    """Degenerate sizes and starts the reference accepts: K = 1 (no iteration), K = 2, an empty batch, a start inside
+    an obstacle (the reference never tests the start), start == goal (found at the first accepted node or never)."""
+    from theta_rrt_b200 import samples
+    from oracle.c_oracle import Params as OP
+    free = maps["map1"]
+    blocked = np.argwhere(~free)[0]
+    starts = np.array([[5.0, 5.0, 0.0], [float(blocked[1]), float(blocked[0]), 90.0], [50.0, 20.0, -180.0]])
+    goals = np.array([[90.0, 50.0, 90.0], [10.0, 10.0, 0.0], [50.0, 20.0, 180.0]])
+    for K in (1, 2, 3, 40):
+        nq = len(starts)
+        sxy = np.empty((nq, max(K - 1, 0), 2), np.int32); sth = np.empty((nq, max(K - 1, 0)))
+        for q in range(nq):
+            sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, 9 + q, free.shape)
+        for lanes, schedule in ((32, 0), (4, 0), (8, 1)):
+            p = planner_for(free)
+            res = p.rrt(starts, goals, sxy, sth, K=K, logs=True, lanes=lanes, schedule=schedule).host()
+            for q in range(nq):
+                o = O.rrt(free, ((starts[q, 0], starts[q, 1]), starts[q, 2]), ((goals[q, 0], goals[q, 1]), goals[q, 2]),
+                          sxy[q], sth[q], OP(), K=K)
+                n = o["n_nodes"]
+                tag = (K, q, lanes, schedule)
+                assert int(res["n_nodes"][q]) == n and int(res["sol"][q]) == o["sol"] and int(res["status"][q]) == o["status"], tag
+                assert int(res["iters"][q]) == o["iters"], tag
+                assert np.array_equal(res["parent"][q, :n], o["parent"]), tag
+                assert bits_equal(res["node_x"][q, :n], o["x"]) and bits_equal(res["node_theta"][q, :n], o["theta"]), tag
+    p = planner_for(free)
+    empty = p.rrt(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 9, 2), np.int32), np.zeros((0, 9)), K=10)
+    assert empty.n_nodes.numel() == 0
+    assert p.theta(np.zeros((0, 4), np.int32)).path_len.numel() == 0
+
+
+def test_rrt_host_pipeline_equals_resident(maps):
+    """Planner.rrt_host (chunked, side streams, pinned buffers) returns exactly what the resident call returns."""
+    import torch
+    from theta_rrt_b200 import samples
+    free = maps["map1"]
+    nq, K = 37, 301
+    starts, goals = util.random_queries(free, nq, 4321)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, 70 + q, free.shape)
+    p = planner_for(free, tol_xy=0.0)
+    ref = p.rrt(starts, goals, sxy, sth, K=K).host()
+    ins = [torch.from_numpy(a).pin_memory() for a in (starts, goals, sxy, sth)]
+    for chunks in (1, 5):
+        out = {"node_x": torch.zeros((nq, K), dtype=torch.float64).pin_memory(), "parent": torch.zeros((nq, K), dtype=torch.int32).pin_memory(),
+               "n_nodes": torch.zeros(nq, dtype=torch.int32).pin_memory(), "u": torch.zeros((nq, K, 5), dtype=torch.float64).pin_memory()}
+        for _ in range(2):  # second call reuses the cached device buffers
+            p.rrt_host(*ins, out=out, K=K, chunks=chunks)
+            torch.cuda.synchronize()
+        assert np.array_equal(out["n_nodes"].numpy(), ref["n_nodes"])
+        for q in range(nq):
+            n = int(ref["n_nodes"][q])
+            assert np.array_equal(out["parent"].numpy()[q, :n], ref["parent"][q, :n])
+            assert bits_equal(out["node_x"].numpy()[q, :n], ref["node_x"][q, :n])
+            assert np.array_equal(out["u"].numpy()[q, 1:n].view(np.int64), ref["u"][q, 1:n].view(np.int64))

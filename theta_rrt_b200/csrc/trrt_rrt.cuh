@@ -385,7 +385,7 @@ __device__ __forceinline__ void nearest_private(const double *__restrict__ nx, c
         int p = 0;
         for (; p + 1 < pairs; p += 2) {
             // the tree streams from L2 / HBM: ask for the lines TRRT_SCAN_AHEAD bytes ahead (one request per 128-byte line)
-            if ((p & 7) == 0) {
+            if ((p & 7) == 0 && p + TRRT_SCAN_AHEAD / 16 < pairs) { // never beyond the nodes that exist
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(x2 + p + TRRT_SCAN_AHEAD / 16));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(y2 + p + TRRT_SCAN_AHEAD / 16));
             }

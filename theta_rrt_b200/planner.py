@@ -162,12 +162,13 @@ class Planner:
             starts = self._dev(starts, torch.float64).reshape(-1, 3)
             goals = self._dev(goals, torch.float64).reshape(-1, 3)
             nq = starts.shape[0]
-            sample_th = self._dev(sample_th, torch.float64).reshape(nq, -1)
+            sample_th = self._dev(sample_th, torch.float64)
             if K is None:
-                K = sample_th.shape[1] + 1
+                K = (sample_th.numel() // nq if nq else 0) + 1
             K = int(K)
-            if sample_th.shape[1] != K - 1:
-                raise ValueError(f"sample stream has {sample_th.shape[1]} iterations, K-1 = {K - 1}")
+            if sample_th.numel() != nq * (K - 1):
+                raise ValueError(f"sample stream has {sample_th.numel()} values, expected {nq} x (K-1 = {K - 1})")
+            sample_th = sample_th.reshape(nq, K - 1)
             sample_xy = self._dev(sample_xy, torch.int32).reshape(nq, K - 1, 2)
             mid = self._map_ids(map_id, nq)
             dev = self.device
