@@ -112,16 +112,14 @@ TL_FN int tl_rem_pio2(double x, double *y0, double *y1) {
 
 TL_ENTRY void tl_sincos(double x, double *s, double *c) {
     double ax = fabs(x);
-    double y0 = x, y1 = 0.0;
-    int n = 0;
-    if (ax > 0.78539816339744827900) {
-        if (!(ax < 1.0e300)) { /* inf / nan / absurd */
-            *s = x - x; *c = x - x; return;
-        }
-        n = tl_rem_pio2(x, &y0, &y1);
-    } else if (ax < 7.450580596923828125e-09 /* 2^-27 */) {
-        *s = x; *c = 1.0; return;
+    double y0, y1;
+    if (!(ax < 1.0e300)) { /* inf / nan / absurd */
+        *s = x - x; *c = x - x; return;
     }
+    if (ax < 7.450580596923828125e-09 /* 2^-27 */) { *s = x; *c = 1.0; return; }
+    /* below pi/4 the reduction is the identity (fn = 0: y0 = x, y1 = +0, n = 0), so it runs unconditionally and the
+       lanes of a warp do not split on the size of their argument */
+    const int n = tl_rem_pio2(x, &y0, &y1);
     double ks = tl_ksin(y0, y1), kc = tl_kcos(y0, y1);
     double ss = (n & 1) ? kc : ks, cc = (n & 1) ? ks : kc;
     /* quadrant signs: n=0 (s,c) n=1 (c,-s) n=2 (-s,-c) n=3 (-c,s) */
@@ -173,23 +171,23 @@ TL_ENTRY double tl_atan2(double y, double x) {
     /* first-quadrant angle a = atan(ay/ax) by angle addition against c in {0, 1/2, 1, 2, inf}:
        atan(ay/ax) = atan(c) + atan(t), t = (ay - c*ax)/(ax + c*ay), |t| <= 7/16.
        c*ax, c*ay and the numerator are exact (Sterbenz); the denominator is carried as dh + dl. */
-    double hi, lo, num, dh, dl;
-    if (ay * 16.0 < ax * 7.0) { /* ratio < 7/16: c = 0 */
-        hi = 0.0; lo = 0.0; num = ay; dh = ax; dl = 0.0;
-    } else if (ay * 4.0 >= ax * 16.0) { /* ratio >= 4: c = inf, atan = pi/2 - atan(ax/ay) */
-        hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17;
-        num = -ax; dh = ay; dl = 0.0;
-    } else {
-        double c;
-        if (ay * 16.0 < ax * 11.0) { c = 0.5; hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17; }
-        else if (ay * 2.0 < ax * 3.0) { c = 1.0; hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17; }
-        else { c = 2.0; hi = 1.10714871779409040897e+00; lo = 9.40447137356637941245e-17; } /* atan(2) */
-        double cx = c * ax, cy = c * ay;
-        num = ay - cx;
-        dh = ax + cy;
-        double bb = dh - ax;             /* TwoSum(ax, cy) */
-        dl = (ax - (dh - bb)) + (cy - bb);
-    }
+    /* The octant is chosen with selects, not branches (lanes of a warp hold unrelated vectors): c = 0 and c = inf run
+       through the general formula with c = 0 -- for c = inf on the swapped pair (-ax, ay) -- which reproduces
+       num = ay (resp. -ax), dh = ax (resp. ay), dl = +0 exactly (0*v = +-0, v - 0 = v, v + +-0 = v). */
+    const int c0 = ay * 16.0 < ax * 7.0;              /* ratio < 7/16: c = 0 */
+    const int cinf = !c0 && (ay * 4.0 >= ax * 16.0);  /* ratio >= 4: c = inf, atan = pi/2 - atan(ax/ay) */
+    const int chalf = ay * 16.0 < ax * 11.0, cone = ay * 2.0 < ax * 3.0;
+    const double c = (c0 | cinf) ? 0.0 : (chalf ? 0.5 : (cone ? 1.0 : 2.0));
+    const double hi = c0 ? 0.0 : (cinf ? 1.57079632679489655800e+00
+                                       : (chalf ? 4.63647609000806093515e-01 : (cone ? 7.85398163397448278999e-01 : 1.10714871779409040897e+00)));
+    const double lo = c0 ? 0.0 : (cinf ? 6.12323399573676603587e-17
+                                       : (chalf ? 2.26987774529616870924e-17 : (cone ? 3.06161699786838301793e-17 : 9.40447137356637941245e-17)));
+    const double yy = cinf ? -ax : ay, xx = cinf ? ay : ax;
+    const double cx = c * xx, cy = c * yy;
+    const double num = yy - cx;
+    const double dh = xx + cy;
+    const double bb = dh - xx;             /* TwoSum(xx, cy) */
+    const double dl = (xx - (dh - bb)) + (cy - bb);
     /* one division: t approximates NUM/DEN, e is the remainder of the exact quotient */
     double rdh = 1.0 / dh;
     double t = num * rdh;
@@ -197,19 +195,13 @@ TL_ENTRY double tl_atan2(double y, double x) {
     double p = tl_atan_poly(t);
     /* atan(t + e) ~= t - p + e*(1 - t*t) (|e| <= ~2 ulp(t), |t| <= 7/16) */
     double small = fma(e, fma(-t, t, 1.0), -p) + lo;
-    double s, rest; /* first-quadrant result = s + rest, |rest| << |s| */
-    if (hi == 0.0) { s = t; rest = small; }
-    else {
-        s = hi + t;                      /* |hi| >= |t| : Fast2Sum */
-        rest = (t - (s - hi)) + small;
-    }
-    double r;
-    if (x > 0.0) r = s + rest;
-    else { /* second/third quadrant: pi - (s + rest) with the low word of pi */
-        double u = TL_PI - s;            /* |pi| >= |s| : Fast2Sum */
-        double ue = (TL_PI - u) - s;
-        r = u + ((ue + TL_PI_LO) - rest);
-    }
+    /* first-quadrant result = s + rest, |rest| << |s|; with hi = 0 this is s = t, rest = small exactly */
+    const double s = hi + t;                 /* |hi| >= |t| or hi = 0 : Fast2Sum */
+    const double rest = (t - (s - hi)) + small;
+    /* second/third quadrant: pi - (s + rest) with the low word of pi */
+    const double u = TL_PI - s;              /* |pi| >= |s| : Fast2Sum */
+    const double ue = (TL_PI - u) - s;
+    const double r = (x > 0.0) ? s + rest : u + ((ue + TL_PI_LO) - rest);
     return (y < 0.0) ? -r : r;
 }
 

@@ -574,9 +574,8 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                     }
                     near_j = g.bcast(near, j);
                     const int ecode = g.bcast(e.code, j), eflags = g.bcast(e.flags, j);
-                    c.scan += (unsigned long long)n;
                     const bool mine = g.gl == j;
-                    if (mine) c.steer++;
+                    if (a.counters) { c.scan += (unsigned long long)n; if (mine) c.steer++; }
                     if (ecode == TRRT_IT_STEER_CONSTRAINT) code = TRRT_IT_STEER_CONSTRAINT;
                     else {
                         const int nl = (eflags >> 4) & 3;
@@ -585,7 +584,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                                 if (nl >= 1) Q.los_log[nlos] = (eflags >> 6) & 1;
                                 if (nl >= 2) Q.los_log[nlos + 1] = (eflags >> 7) & 1;
                             }
-                            c.los += nl; c.lospx += e.lospx; c.arcpx += e.arcpx; c.arcang += e.arcang; c.drive += e.drive;
+                            if (a.counters) { c.los += nl; c.lospx += e.lospx; c.arcpx += e.arcpx; c.arcang += e.arcang; c.drive += e.drive; }
                         }
                         nlos += nl;
                         if (eflags & 2) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; code = TRRT_IT_NOT_RUN; go = false; }
@@ -599,9 +598,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                                     code = TRRT_IT_NEW_NODE;
                                     if (mine) {
                                         Q.nx[idx] = e.wx; Q.ny[idx] = e.wy; Q.nth[idx] = e.wth;
-                                        Q.parent[idx] = -1;
-                                        if (Q.uo) for (int t = 0; t < 5; t++) Q.uo[5 * idx + t] = NAN;
-                                        tree_insert(Q.tab, Q.tmask, e.wx, e.wy, e.wth, idx);
+                                        tree_insert(Q.tab, Q.tmask, e.wx, e.wy, e.wth, idx); // parent / u follow below (a new node is never its own nearest)
                                     }
                                     // every lane folds the new node into its window minimum and equality flags
                                     const double vx = g.bcast(e.wx, j), vy = g.bcast(e.wy, j), vth = g.bcast(e.wth, j);
