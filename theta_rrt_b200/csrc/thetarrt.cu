@@ -647,10 +647,11 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                     const int cnt = g.bcast(np_, t);
                     const double fa = g.bcast(f1, t), fb = g.bcast(f2, t);
                     const unsigned c1 = g.bcast(nbc, t);
-                    if (lead) {
-                        if (!heap_push<G>(heap, hsize, a.heap_cap, fa, c1)) overflow = true;
-                        if (cnt == 2 && !heap_push<G>(heap, hsize, a.heap_cap, fb, c1)) overflow = true;
-                    }
+                    // The reference puts (fa, node) and then, when the grand-parent path is shorter, (fb, node) with
+                    // fb <= fa (search.py:283-304).  The node is closed when its smallest entry is popped and every later
+                    // pop of it is skipped (search.py:250-255), so the (fa, node) entry of such a pair can never act:
+                    // only the smaller key is stored; `pushes` still counts what the reference puts.
+                    if (lead && !heap_push<G>(heap, hsize, a.heap_cap, cnt == 2 ? fb : fa, c1)) overflow = true;
                     npush += cnt;
                 }
                 hsize = g.bcast(hsize, 0);

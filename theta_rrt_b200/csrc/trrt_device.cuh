@@ -106,17 +106,23 @@ __device__ __forceinline__ bool los_group(const Group<G> &g, const Grid &m, long
     int step = low ? ((y1 < y0) ? -1 : 1) : ((x1 < x0) ? -1 : 1);
     unsigned n = dmaj + 1u;
     if (pixels_tested) *pixels_tested += n;
-    unsigned den = dmaj ? 2u * dmaj : 1u;
+    // lane l tests pixels l, l+G, ...: the minor offset s_i = floor((2*dmin*i + dmaj - 1) / (2*dmaj)) is advanced by
+    // G pixels per step with a quotient / remainder pair (one division per ray, none per pixel)
+    const unsigned den = dmaj ? 2u * dmaj : 1u;
+    const unsigned num0 = 2u * dmin * (unsigned)g.gl + dmaj - (dmaj ? 1u : 0u);
+    unsigned s = num0 / den, rem = num0 - s * den;
+    const unsigned inc = 2u * dmin * (unsigned)G, q = inc / den, r = inc - q * den;
     for (unsigned base = 0; base < n; base += G) {
         unsigned i = base + (unsigned)g.gl;
         bool blocked = false;
         if (i < n) {
-            int s = (int)((2u * dmin * i + dmaj - (dmaj ? 1u : 0u)) / den);
-            int px = low ? x0 + (int)i : x0 + step * s;
-            int py = low ? y0 + step * s : y0 + (int)i;
+            int px = low ? x0 + (int)i : x0 + step * (int)s;
+            int py = low ? y0 + step * (int)s : y0 + (int)i;
             blocked = !m.free_nb(px, py);
         }
         if (g.any(blocked)) return false;
+        s += q; rem += r;
+        if (rem >= den) { rem -= den; s++; }
     }
     return true;
 }
