@@ -434,6 +434,12 @@ def test_rrt_host_pipeline_equals_resident(maps):
         for _ in range(2):  # second call reuses the cached device buffers
             p.rrt_host(*ins, out=out, K=K, chunks=chunks)
             torch.cuda.synchronize()
+        for t in out.values():
+            t.zero_()
+        for _ in range(3):  # streamed batches: nothing waits until host_sync()
+            p.rrt_host(*ins, out=out, K=K, chunks=chunks, wait=False)
+        p.host_sync()
+        torch.cuda.synchronize()
         assert np.array_equal(out["n_nodes"].numpy(), ref["n_nodes"])
         for q in range(nq):
             n = int(ref["n_nodes"][q])

@@ -214,13 +214,16 @@ class Planner:
             res._keep = (starts, goals, sample_xy, sample_th, mid)
         return res
 
-    def rrt_host(self, starts, goals, sample_xy, sample_th, out, K=None, chunks=4, **kw):
+    def rrt_host(self, starts, goals, sample_xy, sample_th, out, K=None, chunks=4, wait=True, **kw):
         """rrt.rrt for a batch whose inputs and outputs live in (pinned) HOST memory: the queries are cut into
         `chunks` contiguous pieces, each on its own stream (host->device copy, fused kernel, device->host copy), so
         that the PCIe transfers of one piece overlap the planning of the others.  `out` maps RrtResult field names
         (node_x, node_y, node_theta, parent, u, n_nodes, sol, status, iters, ...) to host tensors with a leading
-        query dimension; they are filled in place.  The call returns after enqueuing; the planner's current stream
-        waits for every piece (synchronise it before reading `out`)."""
+        query dimension; they are filled in place.  The call returns after enqueuing.  With wait=True the planner's
+        current stream waits for every piece (synchronise it before reading `out`).  With wait=False nothing waits:
+        successive calls queue piece c of the next batch behind piece c of this one on the same stream, so the
+        transfers of one batch also overlap the planning of the next (double-buffered streaming of batches); call
+        host_sync() before reading the outputs or reusing the host buffers."""
         ins = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))
                for t in (starts, goals, sample_xy, sample_th)]
         nq = ins[0].shape[0]
@@ -254,9 +257,20 @@ class Planner:
                     keep.append((din, res))
                 done = torch.cuda.Event()
                 done.record(st)
-                main.wait_event(done)
+                if wait:
+                    main.wait_event(done)
+                else:
+                    self._pending = [e for e in getattr(self, "_pending", []) if not e.query()] + [done]
             self._inflight = keep  # tensors stay referenced until the next call
         return out
+
+    def host_sync(self):
+        """Make the planner's current stream wait for every piece enqueued by rrt_host(..., wait=False)."""
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            for e in getattr(self, "_pending", []):
+                main.wait_event(e)
+            self._pending = []
 
     def findnearest(self, res: RrtResult, goals, params=None):
         """rrt.findnearest (rrt.py:117-128) for every query of an RrtResult produced with logs=True."""
