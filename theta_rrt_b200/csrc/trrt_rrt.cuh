@@ -476,10 +476,10 @@ __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE
 #define TRRT_SPEC_LOCKSTEP 1
 #endif
 #ifndef TRRT_SPEC_THREADS
-#define TRRT_SPEC_THREADS 256 /* measured on B200 (cfg 3): 256 x 3 lockstep 75.9 ms, 128 x 4 free-running 81.5 ms, 512 x 1 lockstep 83.6 ms */
+#define TRRT_SPEC_THREADS 384 /* measured on B200 (cfg 3, final kernel): 384 x 2 68.6 ms, 256 x 3 70.2 ms, 256 x 4 73.8 ms; see profiles/r1/NOTES.md */
 #endif
 #ifndef TRRT_SPEC_BLOCKS_PER_SM
-#define TRRT_SPEC_BLOCKS_PER_SM 3
+#define TRRT_SPEC_BLOCKS_PER_SM 2
 #endif
 
 template <int G>
