@@ -41,6 +41,8 @@ sys.path.insert(0, ROOT)
 NQ_PER_GPU = 4096
 K_RRT = 5001
 MAP_SEED = 1234
+WORKLOAD = ("cfg3: batched RRT, %d independent queries per GPU on map1.png (100x100), K=%d "
+            "(5000 expansions each), tol_xy=0, seeded rand_conf streams")
 
 
 # --------------------------------------------------------------------------- workload
@@ -163,7 +165,8 @@ def profile_traffic(kernel):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel)
+            rec = json.load(open(p)).get(kernel)
+            return rec["bytes"] if isinstance(rec, dict) else rec
         except Exception:
             return None
     return None
@@ -194,8 +197,8 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": "rrt_expansions_per_sec", "value": value, "unit": "expansions/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg3: batched RRT on map1.png, 5000 expansions per query, tol_xy=0",
-                       "queries_per_step": nq, "K": K_RRT, "host_threads": cores},
+            "config": {"workload": WORKLOAD % (NQ_PER_GPU, K_RRT), "queries_per_gpu": NQ_PER_GPU, "K": K_RRT,
+                       "sample_queries_per_step": nq, "host_threads": cores},
             "cpu_baseline": {"value": value, "unit": "expansions/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -376,8 +379,7 @@ def main():
     line = {"metric": "rrt_expansions_per_sec", "value": value, "unit": "expansions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg3: batched RRT, %d independent queries per GPU on map1.png (100x100), K=%d "
-                                   "(5000 expansions each), tol_xy=0, seeded rand_conf streams" % (nq, K),
+            "config": {"workload": WORKLOAD % (nq, K),
                        "queries_per_gpu": nq, "K": K, "lanes_per_query": args.lanes or 32,
                        "schedule": "speculative window" if args.schedule == 0 else "cooperative",
                        "parallelism": "query-sharded x%d, no data-path collective" % world,
