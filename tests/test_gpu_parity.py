@@ -446,3 +446,72 @@ def test_rrt_host_pipeline_equals_resident(maps):
             assert np.array_equal(out["parent"].numpy()[q, :n], ref["parent"][q, :n])
             assert bits_equal(out["node_x"].numpy()[q, :n], ref["node_x"][q, :n])
             assert np.array_equal(out["u"].numpy()[q, 1:n].view(np.int64), ref["u"][q, 1:n].view(np.int64))
+
+
+# ------------------------------------------------------------------ BASELINE full sizes: properties + exact subsets
+def test_cfg4_full_size_nearest_and_raycast(O):
+    """BASELINE cfg 4 at full size: 8192 x 8192 grid, 2^20-node tree, 4096 nearest queries, 2^20 rays.
+    Nearest: exact against numpy's first-minimum argmin of the same unfused fp64 expression for 128 of the queries,
+    and for ALL queries the reported d2 equals the recomputed one and no sampled node is nearer.
+    Rays: exact against the oracle on a 10^4 subset, and symmetric (search.py:47-56 canonicalises) on all 2^20."""
+    import bench
+    rng = np.random.default_rng(3)
+    n_nodes, nq = 1 << 20, 4096
+    x, y = rng.uniform(0, 8191, n_nodes), rng.uniform(0, 8191, n_nodes)
+    x[777] = x[123456]; y[777] = y[123456]  # an exact duplicate: the lower index must win
+    qxy = rng.integers(0, 8192, size=(nq, 2)).astype(np.int32)
+    qxy[0] = (int(x[123456]), int(y[123456]))
+    big = bench.synthetic_map(8192, 0.1, 8, 42)
+    p = planner_for(big)
+    idx, d2 = p.nearest(x, y, qxy, want_d2=True)
+    idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
+    for q in range(128):
+        dx, dy = qxy[q, 0] - x, qxy[q, 1] - y
+        assert idx[q] == int(np.argmin(dx * dx + dy * dy)), q
+    dx, dy = qxy[:, 0] - x[idx], qxy[:, 1] - y[idx]
+    assert bits_equal(d2, dx * dx + dy * dy)
+    probe = rng.integers(0, n_nodes, 4096)
+    dd = (qxy[:, 0:1] - x[probe][None, :]) ** 2 + (qxy[:, 1:2] - y[probe][None, :]) ** 2
+    assert (dd.min(axis=1) >= d2).all()
+    seg = bench.make_segments(big, 1 << 20, 7)
+    got = p.los(seg).cpu().numpy().astype(bool)
+    sub = rng.integers(0, len(seg), 10000)
+    assert np.array_equal(got[sub], O.lineofsight_batch(big, seg[sub], threads=4))
+    assert np.array_equal(p.los(seg[:, [2, 3, 0, 1]].copy()).cpu().numpy().astype(bool), got)
+    # a ray is clear iff both halves are clear when split at a pixel of the SAME raster: endpoints free is necessary
+    free_end = big[seg[:, 1], seg[:, 0]] & big[seg[:, 3], seg[:, 2]]
+    assert not (got & ~free_end).any()
+
+
+def test_cfg3_full_depth_batch_properties(O, maps):
+    """BASELINE cfg 3 depth (K = 5001) on a 512-query batch: the result is a well-formed forest, independent of the
+    lane count and of repetition (persistent groups pull queries in a different order every run), and the first and
+    last query of the batch equal the oracle bit for bit."""
+    from theta_rrt_b200 import samples
+    from oracle.c_oracle import Params as OP
+    free = maps["map1"]
+    nq, K = 512, 5001
+    starts, goals = util.random_queries(free, nq, 1234)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, q, free.shape)
+    p = planner_for(free, tol_xy=0.0)
+    a = p.rrt(starts, goals, sxy, sth, K=K, lanes=32).host()
+    b = p.rrt(starts, goals, sxy, sth, K=K, lanes=32).host()
+    c = p.rrt(starts, goals, sxy, sth, K=K, lanes=16).host()
+    for other in (b, c):
+        assert np.array_equal(a["n_nodes"], other["n_nodes"]) and np.array_equal(a["status"], other["status"])
+        assert np.array_equal(a["iters"], other["iters"])
+    for q in range(nq):
+        n = int(a["n_nodes"][q])
+        assert 1 <= n <= K and a["parent"][q, 0] == -1
+        par = a["parent"][q, 1:n]
+        assert (par >= 0).all() and (par < n).all()
+        for other in (b, c):
+            assert np.array_equal(a["parent"][q, :n], other["parent"][q, :n]), q
+            assert bits_equal(a["node_x"][q, :n], other["node_x"][q, :n]) and bits_equal(a["node_theta"][q, :n], other["node_theta"][q, :n]), q
+    for q in (0, nq - 1):
+        o = O.rrt(free, ((starts[q, 0], starts[q, 1]), starts[q, 2]), ((goals[q, 0], goals[q, 1]), goals[q, 2]), sxy[q], sth[q],
+                  OP(tol_xy=0.0), K=K)
+        n = o["n_nodes"]
+        assert int(a["n_nodes"][q]) == n and np.array_equal(a["parent"][q, :n], o["parent"]) and bits_equal(a["node_x"][q, :n], o["x"])
