@@ -501,7 +501,7 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args):
                          "expansions_per_sec": int(r["expanded"][0]) / (ms1 / 1e3)}
     cells = np.argwhere(m2)
     rq = np.random.default_rng(5)
-    nqt = 2048
+    nqt = 8192
     a, b = cells[rq.integers(len(cells), size=nqt)], cells[rq.integers(len(cells), size=nqt)]
     sg = torch.from_numpy(np.stack([a[:, 1], a[:, 0], b[:, 1], b[:, 0]], 1).astype(np.int32)).to(dev)
     msb = timed(lambda: pt.theta(sg, path_cap=64), n=3, warm=1)

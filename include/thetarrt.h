@@ -234,6 +234,10 @@ typedef struct trrt_theta_args {
     int32_t heap_cap;    /* 0 = auto */
     void *d_work;
     size_t work_bytes;
+    /* optional dispatch order: slots take query d_order[0], d_order[1], ... (a permutation of 0..n_queries-1).  Searches
+       differ in length by orders of magnitude and a batch ends with its longest one, so callers that can guess the
+       length (e.g. start-goal distance, longest first) shorten the tail.  Results stay indexed by query.  NULL = 0,1,2,... */
+    const int32_t *d_order;
 } trrt_theta_args;
 
 /* fills in n_slots / heap_cap when 0 and returns the bytes needed */

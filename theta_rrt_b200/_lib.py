@@ -57,6 +57,7 @@ class CThetaArgs(C.Structure):
         ("d_expanded", C.c_void_p), ("d_status", C.c_void_p),
         ("d_los_log", C.c_void_p), ("los_cap", C.c_int32), ("d_n_los", C.c_void_p), ("d_pushes", C.c_void_p),
         ("n_slots", C.c_int32), ("heap_cap", C.c_int32), ("d_work", C.c_void_p), ("work_bytes", C.c_size_t),
+        ("d_order", C.c_void_p),
     ]
 
 

@@ -331,8 +331,10 @@ class Planner:
 
     # ------------------------------------------------------------------ K3
     def theta(self, start_goal, thetastar=None, map_id=None, path_cap=None, log_los=False, lanes=0, n_slots=0,
-              heap_cap=0):
-        """search.astar for queries int32 [q,4] = (sx, sy, gx, gy)."""
+              heap_cap=0, longest_first=True):
+        """search.astar for queries int32 [q,4] = (sx, sy, gx, gy).  longest_first: dispatch the queries to the
+        persistent slots by decreasing start-goal distance (a batch ends with its longest search; results stay
+        indexed by query)."""
         if thetastar is None:
             thetastar = self.params.THETASTAR
         with torch.cuda.device(self.device):
@@ -360,12 +362,17 @@ class Planner:
                                 d_expanded=res.expanded.data_ptr(), d_status=res.status.data_ptr(),
                                 d_los_log=ptr(res.los_log), los_cap=int(los_cap), d_n_los=res.n_los.data_ptr(),
                                 d_pushes=res.pushes.data_ptr(), n_slots=int(n_slots), heap_cap=int(heap_cap),
-                                d_work=None, work_bytes=0)
+                                d_work=None, work_bytes=0, d_order=None)
+            order = None
+            if longest_first and nq > 1:
+                d = (sg[:, 2] - sg[:, 0]).to(torch.float32) ** 2 + (sg[:, 3] - sg[:, 1]).to(torch.float32) ** 2
+                order = torch.argsort(d, descending=True).to(torch.int32)
+                a.d_order = order.data_ptr()
             wb = self.lib.trrt_theta_workspace_bytes(C.byref(a))  # fills n_slots / heap_cap
             work = self._scratch("theta", wb)
             a.d_work = work.data_ptr()
             a.work_bytes = work.numel()
             _lib.check(self.lib.trrt_theta_batch(C.byref(a), self._stream()), "trrt_theta_batch")
             res.extra = dict(n_slots=int(a.n_slots), heap_cap=int(a.heap_cap), workspace_bytes=int(wb))
-            res._keep = (sg, mid)
+            res._keep = (sg, mid, order)
         return res
