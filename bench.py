@@ -180,7 +180,7 @@ def run_reference_arm(args, rank, world):
     from oracle import c_oracle as O
     free = load_maps()["map1"]
     cores = os.cpu_count() or 1
-    nq = max(cores, 8)  # ~0.35 s of one core per query: a step is a few seconds of wall
+    nq = max(4 * cores, 32)  # ~0.2 s of one core per query, four queries per thread: a step is about a second of wall
     starts, goals, sxy, sth = make_rrt_workload(free, nq, K_RRT)
     P = O.Params(tol_xy=0.0)
     O.lib()
