@@ -69,13 +69,18 @@ __device__ __noinline__ bool arc_blocked_lane(const Grid &m, double bx, double b
     // when the span is below 180 degrees they lie in the convex cone spanned by begin-icc and land-icc.
     const double rout = rad + 2.5, rin = fmax(rad - 3.5, 0.0);
     double xlo = -rout, xhi = rout, ylo = -rout, yhi = rout;
-    if (A.diff_lt_180 == 1 && A.n1 > 0.0 && A.n2 > 0.0) {
-        const double s1 = 1.0 / sqrt(A.n1), s2 = 1.0 / sqrt(A.n2);
-        const double d1x = A.u1x * s1, d1y = A.u1y * s1, d2x = A.u2x * s2, d2y = A.u2y * s2;
-        xlo = fmin(fmin(d1x * rin, d1x * rout), fmin(d2x * rin, d2x * rout));
-        xhi = fmax(fmax(d1x * rin, d1x * rout), fmax(d2x * rin, d2x * rout));
-        ylo = fmin(fmin(d1y * rin, d1y * rout), fmin(d2y * rin, d2y * rout));
-        yhi = fmax(fmax(d1y * rin, d1y * rout), fmax(d2y * rin, d2y * rout));
+    // begin and land both lie on the circle (rad = |begin - icc| by construction, land is begin rotated about icc), so
+    // u / rad is their direction; if that ever failed by more than rounding the full box is used
+    const double rr2 = rad * rad;
+    if (A.diff_lt_180 == 1 && rad > 0.0 && fabs(A.n1 - rr2) <= 1e-6 * rr2 && fabs(A.n2 - rr2) <= 1e-6 * rr2) {
+        const double inv = 1.0 / rad, kin = rin * inv, kout = rout * inv;
+        // extent of the two boundary rays between the radii: a coordinate c of u spans [c*kin, c*kout] (or reversed)
+        const double x1a = A.u1x * (A.u1x < 0 ? kout : kin), x1b = A.u1x * (A.u1x < 0 ? kin : kout);
+        const double x2a = A.u2x * (A.u2x < 0 ? kout : kin), x2b = A.u2x * (A.u2x < 0 ? kin : kout);
+        const double y1a = A.u1y * (A.u1y < 0 ? kout : kin), y1b = A.u1y * (A.u1y < 0 ? kin : kout);
+        const double y2a = A.u2y * (A.u2y < 0 ? kout : kin), y2b = A.u2y * (A.u2y < 0 ? kin : kout);
+        xlo = x1a < x2a ? x1a : x2a; xhi = x1b > x2b ? x1b : x2b;
+        ylo = y1a < y2a ? y1a : y2a; yhi = y1b > y2b ? y1b : y2b;
         // axis directions inside the cone reach the outer radius (sign convention of arc_keeps_pixel)
         const double sg = (usteer > 0) ? 1.0 : -1.0;
         const double ax_ = sg * A.u1x, ay_ = sg * A.u1y, bx_ = sg * A.u2x, by_ = sg * A.u2y;

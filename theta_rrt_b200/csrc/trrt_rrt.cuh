@@ -222,6 +222,7 @@ __device__ __forceinline__ void rrt_setup(const RrtDev &a, int64_t q, const Grou
     Q.los_log = a.los_log ? a.los_log + q * (int64_t)(K - 1) * 2 : nullptr;
     Q.tab = a.tab + q * (int64_t)a.tsize;
     Q.tmask = a.tsize - 1;
+#pragma unroll 4
     for (int i = g.gl; i < a.tsize; i += G) Q.tab[i] = 0;
     Q.gx = a.goal[3 * q]; Q.gy = a.goal[3 * q + 1]; Q.gth = standardangle(a.goal[3 * q + 2]);
     if (g.gl == 0) {
@@ -275,10 +276,13 @@ template <int G>
 __device__ __forceinline__ void rrt_finish(const RrtDev &a, int64_t q, const Group<G> &g, const RrtQuery &Q, int K, int iters, int n, int sol,
                                            int status, int nlos, const RrtCounters &c) {
     if (g.gl == 0) {
-        for (int i = iters; i < K - 1; i++) {
-            if (Q.it_near) Q.it_near[i] = -1;
-            if (Q.it_new) Q.it_new[i] = -1;
-            if (Q.it_code) Q.it_code[i] = TRRT_IT_NOT_RUN;
+        if (Q.it_near || Q.it_new || Q.it_code) {
+#pragma unroll 1
+            for (int i = iters; i < K - 1; i++) {
+                if (Q.it_near) Q.it_near[i] = -1;
+                if (Q.it_new) Q.it_new[i] = -1;
+                if (Q.it_code) Q.it_code[i] = TRRT_IT_NOT_RUN;
+            }
         }
         a.n_nodes[q] = n;
         a.sol[q] = sol;
@@ -409,6 +413,7 @@ __device__ __forceinline__ void nearest_private(const double *__restrict__ nx, c
         }
         i += 2 * pairs;
     }
+#pragma unroll 1
     for (; i < n; i++) TRRT_NODE(nx[i], ny[i], i);
 #undef TRRT_NODE
     bd_out = bd; bi_out = bi;
@@ -470,6 +475,7 @@ __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE
         }
         i += 2 * pairs;
     }
+#pragma unroll 1
     for (; i < n; i++) TRRT_NODE(nx[i], ny[i], i);
 #undef TRRT_NODE
     bd_out = bd; bi_out = bi;
