@@ -1,7 +1,7 @@
 set -e
-for cfg in "__forceinline__" "__noinline__"; do
-  python theta_rrt_b200/build.py -DTRRT_EXPAND_INLINE=$cfg > /dev/null 2>&1
-  python bench.py --steps 3 --warmup 3 --skip-secondary --skip-cpu > gpurun_out/sw_x.json 2>gpurun_out/sw.err
+for b2 in 1 0; do
+  python theta_rrt_b200/build.py -DTRRT_SPEC_BARRIER2=$b2 > /dev/null 2>&1
+  python bench.py --steps 5 --warmup 3 --skip-secondary --skip-cpu > gpurun_out/sw_x.json 2>gpurun_out/sw.err
   python -c "
-import json;d=json.loads(open('gpurun_out/sw_x.json').read().strip().splitlines()[-1]);print('$cfg','ms',round(d['ms_per_step'],2),'Mexp/s',round(d['value']/1e6,1),'e2e',round(d['e2e']['value']/1e6,1))"
+import json;d=json.loads(open('gpurun_out/sw_x.json').read().strip().splitlines()[-1]);print('barrier2',$b2,'ms',round(d['ms_per_step'],2),'Mexp/s',round(d['value']/1e6,1),'e2e',round(d['e2e']['value']/1e6,1))"
 done
