@@ -515,3 +515,25 @@ def test_cfg3_full_depth_batch_properties(O, maps):
                   OP(tol_xy=0.0), K=K)
         n = o["n_nodes"]
         assert int(a["n_nodes"][q]) == n and np.array_equal(a["parent"][q, :n], o["parent"]) and bits_equal(a["node_x"][q, :n], o["x"])
+
+
+@pytest.mark.parametrize("ps", [
+    dict(bikelength=3, LEFTCONSTRAINT=-40, RIGHTCONSTRAINT=40, frontclearance=1.5, maxdrivedist=12, weightxy=0.3, tol_ang=20),
+    dict(FORWARDONLY=False, bikelength=7, LEFTCONSTRAINT=-30, RIGHTCONSTRAINT=55, maxdrivedist=45, weightxy=0.9),
+    dict(tol_xy=25.0, tol_ang=90.0),  # generous goal test: most queries end with a solution
+], ids=["short-bike", "reverse-allowed", "easy-goal"])
+def test_rrt_other_parameters_bitwise_vs_oracle(O, maps, ps):
+    """builtins.* parameters away from the defaults (main.py:15-32), both schedules, bitwise vs the oracle."""
+    from theta_rrt_b200 import samples
+    free = maps["map1"]
+    nq, K = 24, 601
+    starts, goals = util.random_queries(free, nq, 2024)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, 300 + q, free.shape)
+    params = dict(tol_xy=0.0)
+    params.update(ps)
+    for lanes, schedule in ((32, 0), (8, 0), (16, 1)):
+        res = run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, schedule=schedule, **params)
+    if "tol_xy" in ps:
+        assert (res["status"] == 0).sum() > 0 and (res["sol"] >= 0).sum() == (res["status"] == 0).sum()

@@ -110,3 +110,36 @@ def test_findnearest_live(L, maps):
     ep = [index[p] for p in keys for c in G[p]]; ec = [index[c] for p in keys for c in G[p]]
     b, d = O.findnearest([k[0][0] for k in keys], [k[0][1] for k in keys], [k[1] for k in keys], ep, ec, goal)
     assert b == index[node] and abs(d - dist) < 1e-9
+
+
+PARAM_SETS = [
+    dict(bikelength=3, LEFTCONSTRAINT=-40, RIGHTCONSTRAINT=40, frontclearance=1.5, maxdrivedist=12, weightxy=0.3, tol_ang=20),
+    dict(FORWARDONLY=False, bikelength=7, LEFTCONSTRAINT=-30, RIGHTCONSTRAINT=55, maxdrivedist=45, weightxy=0.9),
+]
+
+
+@pytest.mark.parametrize("ps", PARAM_SETS, ids=["short-bike", "reverse-allowed"])
+def test_rrt_live_other_parameters(L, maps, ps):
+    """The builtins.* parameters (main.py:15-32) away from their defaults: the oracle follows the live reference on
+    every discrete output up to the first iteration its margin audit marks as decided by rounding noise."""
+    L.set_map(maps["map1"])
+    goal, start, K = ((80, 20), -45.0), ((10, 90), 30.0), 601
+    st = L.make_stream(goal, K - 1, 5)
+    ref = L.run_rrt(start, goal, st, K=K, tol_xy=0, **ps)
+    L.set_params()
+    sxy = np.array([s[0] for s in st], np.int32); sth = np.array([s[1] for s in st])
+    op = O.Params(tol_xy=0.0, **{k.lower(): (int(v) if isinstance(v, bool) else v) for k, v in ps.items()})
+    o = O.rrt(maps["map1"], start, goal, sxy, sth, op, K=K, audit_eps=util.AUDIT_EPS)
+    if "raised" in ref and ref["raised"]:
+        assert o["status"] == 4
+        return
+    fa = o["first_ambiguous"]
+    near_ref = [i for _, i in ref["nearest"]]
+    near_got = [int(v) for v in o["it_near"] if v >= 0]
+    if fa < 0:
+        assert o["n_nodes"] == ref["n_nodes"] and list(o["parent"]) == ref["parent"]
+        assert near_got == near_ref and list(o["los"]) == [b for _, b in ref["los"]]
+    else:
+        n_cmp = sum(1 for it, _ in ref["nearest"] if it <= fa)
+        assert near_got[:n_cmp] == near_ref[:n_cmp]
+    assert o["n_nodes"] > 20  # the run really grew a tree under these parameters
