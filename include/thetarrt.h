@@ -138,8 +138,9 @@ typedef struct trrt_rrt_args {
     int64_t n_queries;
     int32_t K;
     int32_t lanes_per_query; /* 0 = auto; else 1,2,4,8,16,32 */
-    int32_t schedule;        /* 0 = speculative window of `lanes` iterations (default), 1 = cooperative per iteration;
-                                both give identical results */
+    int32_t schedule;        /* 0 = speculative window of `lanes` iterations in one persistent kernel (default),
+                                1 = cooperative per iteration, 2 = the window of 32 iterations as three kernels per
+                                window over all queries (lanes must be 0 or 32); all give identical results */
     int32_t reserved0;
     const double *d_start;   /* [n_queries][3] = x, y, theta_deg (rrt.py:132) */
     const double *d_goal;    /* [n_queries][3]                    (rrt.py:133) */

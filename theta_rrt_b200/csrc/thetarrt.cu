@@ -23,6 +23,7 @@
 #include "trrt_bike.cuh"
 #include "trrt_device.cuh"
 #include "trrt_rrt.cuh"
+#include "trrt_wave.cuh"
 
 using namespace trrt;
 
@@ -846,7 +847,8 @@ static int rrt_tsize(int K) {
 }
 size_t trrt_rrt_workspace_bytes(int64_t n_queries, int32_t K) {
     if (n_queries <= 0 || K <= 0) return 256;
-    return 256 + (size_t)n_queries * (size_t)rrt_tsize(K) * sizeof(int32_t); // [work counter | hash tables]
+    // [work counter | hash tables | window records of the phase-split schedule]
+    return 256 + (size_t)n_queries * (size_t)rrt_tsize(K) * sizeof(int32_t) + wave_bytes(n_queries);
 }
 
 static BikeParams to_dev(const trrt_params &p) {
@@ -933,6 +935,18 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         RrtDev *dp = &d;
         void *kargs[] = {(void *)dp};
         CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
+    } else if (A.schedule == 2) { // phase-split: three kernels per window over all queries (trrt_wave.cuh)
+        if (G != 32) return TRRT_ERR_INVALID_ARGUMENT;
+        const WaveDev w = wave_carve((char *)A.d_work + 256 + (size_t)A.n_queries * d.tsize * sizeof(int32_t), A.n_queries);
+        const unsigned gw = (unsigned)((A.n_queries * 32 + TRRT_WAVE_THREADS - 1) / TRRT_WAVE_THREADS);
+        const unsigned gs = (unsigned)((A.n_queries * 32 + TRRT_WAVE_SMALL - 1) / TRRT_WAVE_SMALL);
+        CUDA_TRY(cudaMemsetAsync(d.next_query, 0, 2 * sizeof(unsigned long long), st));
+        wave_init<<<gw, TRRT_WAVE_THREADS, 0, st>>>(d, w);
+        for (int k0 = 0; k0 < A.K - 1; k0 += 32) {
+            wave_scan<<<gw, TRRT_WAVE_THREADS, 0, st>>>(d, w, k0);
+            wave_expand<<<gs, TRRT_WAVE_SMALL, 0, st>>>(d, w);
+            wave_commit<<<gs, TRRT_WAVE_SMALL, 0, st>>>(d, w, k0);
+        }
     } else return TRRT_ERR_INVALID_ARGUMENT;
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;

@@ -206,8 +206,8 @@ struct RrtQuery {
     double gx, gy, gth;
 };
 
-template <int G>
-__device__ __forceinline__ void rrt_setup(const RrtDev &a, int64_t q, const Group<G> &g, RrtQuery &Q) {
+// pointers of query q (no memory is touched)
+__device__ __forceinline__ void rrt_ptrs(const RrtDev &a, int64_t q, RrtQuery &Q) {
     const int K = a.K;
     Q.m.W = a.W; Q.m.H = a.H; Q.m.wpr = a.wpr;
     Q.m.bits = a.bits + (a.map_id ? (size_t)a.map_id[q] * a.H * a.wpr : 0);
@@ -222,9 +222,15 @@ __device__ __forceinline__ void rrt_setup(const RrtDev &a, int64_t q, const Grou
     Q.los_log = a.los_log ? a.los_log + q * (int64_t)(K - 1) * 2 : nullptr;
     Q.tab = a.tab + q * (int64_t)a.tsize;
     Q.tmask = a.tsize - 1;
+    Q.gx = a.goal[3 * q]; Q.gy = a.goal[3 * q + 1]; Q.gth = standardangle(a.goal[3 * q + 2]);
+}
+
+// pointers + empty index + the start node (rrt.py:132-138)
+template <int G>
+__device__ __forceinline__ void rrt_setup(const RrtDev &a, int64_t q, const Group<G> &g, RrtQuery &Q) {
+    rrt_ptrs(a, q, Q);
 #pragma unroll 4
     for (int i = g.gl; i < a.tsize; i += G) Q.tab[i] = 0;
-    Q.gx = a.goal[3 * q]; Q.gy = a.goal[3 * q + 1]; Q.gth = standardangle(a.goal[3 * q + 2]);
     if (g.gl == 0) {
         Q.nx[0] = a.start[3 * q]; Q.ny[0] = a.start[3 * q + 1]; Q.nth[0] = standardangle(a.start[3 * q + 2]);
         Q.parent[0] = -1;
