@@ -38,7 +38,7 @@ def test_trivial_host_calls():
     lib.trrt_default_params(C.byref(p))
     assert (p.thetastar, p.forwardonly, p.bikelength, p.leftconstraint, p.rightconstraint) == (1, 1, 5, -65, 65)
     assert (p.frontclearance, p.maxdrivedist, p.tol_xy, p.tol_ang, p.weightxy) == (2, 30, 10, 45, .6)
-    assert lib.trrt_rrt_workspace_bytes(4096, 5001) == 4096 * 16384 * 4 + 256 + (4096 * 32 * (9 * 4 + 12 * 8) + 4096 * (6 * 4 + 8 * 8) + 256)
+    assert lib.trrt_rrt_workspace_bytes(4096, 5001) == 4096 * 16384 * 4 + 256 + (4096 * 32 * (17 * 4 + 20 * 8) + 4096 * (6 * 4 + 8 * 8) + 256)
 
 
 def test_struct_layouts_match_header():

@@ -935,6 +935,7 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         for (int k0 = 0; k0 < A.K - 1; k0 += 32) {
             wave_scan<<<gw, TRRT_WAVE_THREADS, 0, st>>>(d, w, k0);
             wave_expand<<<gs, TRRT_WAVE_SMALL, 0, st>>>(d, w);
+            wave_reexpand<<<gs, TRRT_WAVE_SMALL, 0, st>>>(d, w);
             wave_commit<<<gs, TRRT_WAVE_SMALL, 0, st>>>(d, w, k0);
         }
     } else return TRRT_ERR_INVALID_ARGUMENT;

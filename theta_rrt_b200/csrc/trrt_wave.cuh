@@ -11,12 +11,15 @@
 // and occupancy it needs.  The window state travels through a record per lane in the workspace (SoA, lane fastest).
 // Same arithmetic, same commit order: results are bit-identical to the other two schedules.
 //
-// STATUS (round 1): correct and parity-tested, but EXPERIMENTAL and not the default -- 121 ms per cfg-3 step against
-// 69 ms for the persistent kernel.  Per window (ncu, mid-run): scan 141 us, expand 119 us, commit 439 us.  The commit
-// kernel is the problem: 2.9% of the iterations (0.92 per window and query) find a node of their own window nearer
-// than their snapshot winner and are re-expanded by one lane, and in this kernel that path runs on a cold instruction
-// cache (~85 us per event).  Next step: predict those lanes before the commit and re-expand them in a
-// second, GPU-wide expansion launch.
+// STATUS (round 1): correct and parity-tested, but EXPERIMENTAL and not the default -- 105 ms per cfg-3 step against
+// 69 ms for the persistent kernel.  Per window (ncu, mid-run): scan 141 us, expand 117 us, re-expand 56 us, commit
+// 292 us.  2.9% of the iterations (0.92 per window and query) find a node of their own window nearer than their
+// snapshot winner; wave_reexpand predicts them from the tentative nodes and expands them GPU-wide, which took the
+// one-lane expansions out of the commit (39 M -> 26 M instructions).  What is left in the commit is a serial chain
+// of dependent memory operations that walks ALL queries once per window: the hash-table probe of tree_insert alone
+// is 17% of its warp time at ~3000 cycles per load -- every access lands on a page and an L2 line the SM has not
+// seen since the previous window (2 GB of per-query state against the persistent kernel's few pages per warp).
+// To make this schedule win, the window-hot state of a query (index slots, tail of the tree) has to be packed.
 #pragma once
 #include "trrt_rrt.cuh"
 
@@ -27,12 +30,16 @@ struct WaveDev {
     int *pre, *near, *exist, *code, *flags, *aux; // aux packs drive | lospx<<1 .. (counters only)
     double *bd, *qx, *qy, *qth, *wx, *wy, *wth, *usteer, *iccx, *iccy, *rad, *udist;
     int *lospx, *arcpx, *arcang;
+    // per lane, second expansion of the lanes predicted to be re-expanded (wave_reexpand): from = lane whose tentative
+    // node it starts from (-1 = none)
+    int *a_from, *a_code, *a_flags, *a_exist, *a_aux, *a_lospx, *a_arcpx, *a_arcang;
+    double *a_wx, *a_wy, *a_wth, *a_usteer, *a_iccx, *a_iccy, *a_rad, *a_udist;
     // per query [nq]
     int *n, *nlos, *sol, *status, *iters, *active;
     unsigned long long *cnt; // [nq][8]
 };
 
-#define TRRT_WAVE_LANE_BYTES (9 * 4 + 12 * 8)
+#define TRRT_WAVE_LANE_BYTES (17 * 4 + 20 * 8)
 #define TRRT_WAVE_QUERY_BYTES (6 * 4 + 8 * 8)
 
 __host__ __device__ inline size_t wave_bytes(int64_t nq) {
@@ -42,10 +49,12 @@ inline WaveDev wave_carve(void *base, int64_t nq) {
     WaveDev w;
     char *p = (char *)base;
     const size_t L = (size_t)nq * 32;
-    double **dbl[] = {&w.bd, &w.qx, &w.qy, &w.qth, &w.wx, &w.wy, &w.wth, &w.usteer, &w.iccx, &w.iccy, &w.rad, &w.udist};
+    double **dbl[] = {&w.bd, &w.qx, &w.qy, &w.qth, &w.wx, &w.wy, &w.wth, &w.usteer, &w.iccx, &w.iccy, &w.rad, &w.udist,
+                      &w.a_wx, &w.a_wy, &w.a_wth, &w.a_usteer, &w.a_iccx, &w.a_iccy, &w.a_rad, &w.a_udist};
     for (double **d : dbl) { *d = (double *)p; p += L * 8; }
     w.cnt = (unsigned long long *)p; p += (size_t)nq * 64;
-    int **il[] = {&w.pre, &w.near, &w.exist, &w.code, &w.flags, &w.aux, &w.lospx, &w.arcpx, &w.arcang};
+    int **il[] = {&w.pre, &w.near, &w.exist, &w.code, &w.flags, &w.aux, &w.lospx, &w.arcpx, &w.arcang,
+                  &w.a_from, &w.a_code, &w.a_flags, &w.a_exist, &w.a_aux, &w.a_lospx, &w.a_arcpx, &w.a_arcang};
     for (int **d : il) { *d = (int *)p; p += L * 4; }
     int **iq[] = {&w.n, &w.nlos, &w.sol, &w.status, &w.iters, &w.active};
     for (int **d : iq) { *d = (int *)p; p += (size_t)nq * 4; }
@@ -126,6 +135,53 @@ __global__ void __launch_bounds__(TRRT_WAVE_SMALL) wave_expand(const RrtDev a, c
     w.usteer[s] = e.usteer; w.iccx[s] = e.iccx; w.iccy[s] = e.iccy; w.rad[s] = e.rad; w.udist[s] = e.udist;
 }
 
+// one warp per query: predict the lanes that the commit will have to re-expand, and re-expand them now, all queries
+// at once.  Lane j is re-expanded when a node inserted earlier in its window is strictly nearer than its snapshot
+// winner.  The nodes of the window are not known yet, but the TENTATIVE ones are: lane i will insert (wx_i, wy_i) if
+// its edge was accepted and its node is new.  So lane j takes the nearest tentative node of the lanes i < j (first
+// minimum, like the commit) and, if it beats the snapshot winner, expands from it.  The commit checks the prediction
+// (same lane, and that lane really inserted its tentative node) and falls back to its own one-lane expansion otherwise.
+__global__ void __launch_bounds__(TRRT_WAVE_SMALL) wave_reexpand(const RrtDev a, const WaveDev w) {
+    const Group<32> g;
+    const Group<1> solo;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (q >= a.nq || !w.active[q]) return;
+    const int64_t s = q * 32 + g.gl;
+    const int pre = w.pre[s];
+    const double qx = w.qx[s], qy = w.qy[s];
+    const double bd = (pre == -1) ? w.bd[s] : INFINITY;
+    const bool tentative = (pre == -1) && w.code[s] == EX_ACCEPT && w.exist[s] < 0;
+    const double mx = w.wx[s], my = w.wy[s];
+    double best = INFINITY;
+    int from = -1;
+    const unsigned acc = g.ballot(tentative);
+    for (unsigned m = acc; m; m &= m - 1) { // lanes with a tentative node, in iteration order
+        const int i = __ffs(m) - 1;
+        const double vx = g.bcast(mx, i), vy = g.bcast(my, i);
+        if (i < g.gl) {
+            const double dx = qx - vx, dy = qy - vy;
+            const double d = dx * dx + dy * dy;
+            if (d < best) { best = d; from = i; }
+        }
+    }
+    if (pre != -1 || !(best < bd)) from = -1;
+    w.a_from[s] = from;
+    if (from >= 0) {
+        RrtQuery Q;
+        rrt_ptrs(a, q, Q);
+        const int64_t sf = q * 32 + from;
+        Expand e;
+        unsigned long long probes = 0;
+        expand_from<1>(solo, Q.m, a.P, w.wx[sf], w.wy[sf], w.wth[sf], qx, qy, w.qth[s], Q.gx, Q.gy, Q.gth, e);
+        int exist = -1;
+        if (e.code == EX_ACCEPT) exist = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes);
+        w.a_code[s] = e.code; w.a_flags[s] = e.flags; w.a_exist[s] = exist; w.a_aux[s] = e.drive;
+        w.a_lospx[s] = e.lospx; w.a_arcpx[s] = e.arcpx; w.a_arcang[s] = e.arcang;
+        w.a_wx[s] = e.wx; w.a_wy[s] = e.wy; w.a_wth[s] = e.wth;
+        w.a_usteer[s] = e.usteer; w.a_iccx[s] = e.iccx; w.a_iccy[s] = e.iccy; w.a_rad[s] = e.rad; w.a_udist[s] = e.udist;
+    }
+}
+
 // one warp per query: commit the window in iteration order (phase B of rrt_kernel_spec, same code path)
 __global__ void __launch_bounds__(TRRT_WAVE_SMALL) wave_commit(const RrtDev a, const WaveDev w, const int k0) {
     const Group<32> g;
@@ -146,7 +202,9 @@ __global__ void __launch_bounds__(TRRT_WAVE_SMALL) wave_commit(const RrtDev a, c
     e.wx = w.wx[s]; e.wy = w.wy[s]; e.wth = w.wth[s];
     e.usteer = w.usteer[s]; e.iccx = w.iccx[s]; e.iccy = w.iccy[s]; e.rad = w.rad[s]; e.udist = w.udist[s];
     double wbest = INFINITY;
-    int widx = -1;
+    int widx = -1, wlane = -1;     // nearest node inserted earlier in this window, and the lane that inserted it
+    const int a_from = w.a_from[s];
+    unsigned changed = 0;          // lanes whose committed expansion is not their first one (uniform)
     int n = w.n[q], nlos = w.nlos[q], sol = w.sol[q], status = w.status[q], iters = w.iters[q];
     RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long probes = 0;
@@ -163,11 +221,24 @@ __global__ void __launch_bounds__(TRRT_WAVE_SMALL) wave_commit(const RrtDev a, c
             if (in_tree_j) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
             else {
                 if (g.bcast((int)(wbest < bd), j)) {
-                    // a node of this window is strictly nearer: lane j redoes its iteration from it
-                    g.sync();
+                    // a node of this window is strictly nearer: lane j's iteration starts from it.  wave_reexpand has
+                    // usually done that expansion already; it is valid if it started from the tentative node of the
+                    // same lane and that lane committed its first expansion.
+                    const int wl = g.bcast(wlane, j);
+                    const bool predicted = g.bcast((int)(a_from == wlane), j) && !((changed >> wl) & 1u);
+                    changed |= 1u << j;
+                    g.sync(); // nodes written by earlier steps are visible to lane j
                     if (g.gl == j) {
                         near = widx;
-                        expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
+                        if (predicted) {
+                            e.code = w.a_code[s]; e.flags = w.a_flags[s]; e.drive = w.a_aux[s];
+                            e.lospx = w.a_lospx[s]; e.arcpx = w.a_arcpx[s]; e.arcang = w.a_arcang[s];
+                            e.wx = w.a_wx[s]; e.wy = w.a_wy[s]; e.wth = w.a_wth[s];
+                            e.usteer = w.a_usteer[s]; e.iccx = w.a_iccx[s]; e.iccy = w.a_iccy[s]; e.rad = w.a_rad[s]; e.udist = w.a_udist[s];
+                        } else {
+                            expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
+                        }
+                        // the index now also holds the nodes of this window: one probe answers `qnew in G`
                         exist = -1;
                         if (e.code == EX_ACCEPT) exist = tree_find(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes);
                     }
@@ -204,7 +275,7 @@ __global__ void __launch_bounds__(TRRT_WAVE_SMALL) wave_commit(const RrtDev a, c
                                 if (g.gl > j) {
                                     const double dx = qx - vx, dy = qy - vy;
                                     const double d = dx * dx + dy * dy;
-                                    if (d < wbest) { wbest = d; widx = idx; }
+                                    if (d < wbest) { wbest = d; widx = idx; wlane = j; }
                                     if (qx == vx && qy == vy && qth == vth) q_in_tree = true;
                                     if (exist < 0 && e.wx == vx && e.wy == vy && e.wth == vth) exist = idx;
                                 }
