@@ -2,13 +2,16 @@
 //
 // Kernels (one section each):
 //   pack_grid_kernel      byte image -> bit-packed occupancy grid
-//   los_batch_kernel      K4: search.lineofsight for independent segments
-//   nearest_tile_kernel   K1: fp64 argmin over SoA tree, query-tiled
+//   los_batch_kernel      K4: search.lineofsight for independent segments, one thread per ray
+//   los_group_kernel<G>       same, G lanes per ray (optional)
+//   nearest_tile_kernel   K1: fp64 argmin over SoA tree; query sets in registers, node slices per warp
 //   nearest_final_kernel      cross-slice reduction with lowest-index ties
-//   rrt_kernel_spec<G>    K2: fused rrt.rrt loop, speculative window of G iterations (trrt_rrt.cuh)
+//   rrt_kernel_spec<G>    K2: fused rrt.rrt loop, speculative window of G iterations, persistent (trrt_rrt.cuh)
 //   rrt_kernel_coop<G>        same loop, G lanes cooperating on one iteration at a time
+//   wave_*                    same loop as scan / expand / re-expand / commit kernels (trrt_wave.cuh, experimental)
+//   steer / drive / arc batch kernels: single steps of K2 for the drop-in helpers and step-level parity tests
 //   findnearest_kernel    rrt.findnearest over the edge log
-//   theta_kernel<G>       K3: A* / lazy Theta*, G lanes per query
+//   theta_kernel<G>       K3: A* / lazy Theta*, G lanes per query, G-ary heap
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
 // (see theta_rrt_b200/build.py).  No tensor cores: nothing here is a dense

@@ -420,24 +420,6 @@ __device__ __noinline__ bool arc_keeps_pixel(ArcTest &A, double bx, double by, d
     return fob || bog;
 }
 
-// number of candidate pixels arc_blocked() would enumerate for this circle (rows in range x 2 mirrors)
-__device__ __noinline__ long long arc_candidates(const Grid &m, double iccx, double iccy, double rad) {
-    long long xc = trunc_ll(iccx), yc = trunc_ll(iccy), r = trunc_ll(rad);
-    long long tmax = circle_tmax(r);
-    long long lo[4], hi[4];
-    lo[0] = -yc;             hi[0] = (long long)m.W - 1 - yc;
-    lo[1] = yc - (m.W - 1);  hi[1] = yc;
-    lo[2] = -xc;             hi[2] = (long long)m.H - 1 - xc;
-    lo[3] = xc - (m.H - 1);  hi[3] = xc;
-    long long total = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        long long a = lo[k] < 0 ? 0 : lo[k], b = hi[k] > tmax ? tmax : hi[k];
-        if (b >= a) total += (b - a + 1) * 2;
-    }
-    return total;
-}
-
 // rrt.py:173-174 for a curved edge: is any pixel of getArc(begin, land, u) not free?
 // Candidate circle pixels are enumerated lane-parallel; only blocked in-bounds
 // pixels pay for the angular test (free pixels cannot change the answer).
@@ -522,8 +504,8 @@ __device__ __noinline__ bool arc_blocked_impl(const Group<G> &g, const Grid &m, 
     return false;
 }
 
-// One raster instantiation per use: a lane alone (G == 1, speculative phase) runs the 32-bit version and
-// must not be given radii >= 32768 (callers hand those to the group); groups run the 64-bit version.
+// The generic raster (cooperative schedule, single-step kernel, enormous radii): a lane alone runs the 32-bit version
+// when the radius allows, groups run the 64-bit version.  The speculative schedule uses arc_blocked_lane (trrt_lane.cuh).
 template <int G>
 __device__ __forceinline__ bool arc_blocked(const Group<G> &g, const Grid &m, double bx, double by, double lx, double ly,
                                             double usteer, double iccx, double iccy, double rad,

@@ -1,6 +1,6 @@
 // trrt_rrt.cuh -- K2: the fused rrt.rrt loop (rrt.py:130-206), G lanes per query.
 //
-// Two schedules produce bit-identical results:
+// Three schedules produce bit-identical results:
 //
 //  * cooperative (schedule 1): the G lanes of a group work on ONE loop iteration at a time: the
 //    nearest scan, the Bresenham rays and the circle raster are lane-parallel, the scalar steer /
@@ -9,15 +9,17 @@
 //  * speculative window (schedule 0, default): the sample stream does not depend on the tree
 //    (rrt.py:144 draws before any test), and everything an iteration does after picking its
 //    nearest node depends only on (nearest node, sample, map).  So lane j of a group expands
-//    iteration k0+j against a SNAPSHOT of the tree (n0 nodes at the window start): its own fp64
-//    nearest scan (node loads are warp-uniform broadcasts, so the tree is read once per G
-//    iterations), steer, clearance rays, re-drive and edge raster.  The window is then committed
-//    in iteration order: `qrand in G` and `qnew in G` are answered by the hash index (which
-//    includes nodes inserted earlier in the window), and the snapshot nearest is corrected against
-//    the <= G nodes inserted earlier in the window (new nodes have higher indices, so the snapshot
-//    winner keeps ties).  Only when one of those nodes is strictly nearer (about 3% of iterations
-//    at G = 32 on map1) is the iteration recomputed, cooperatively, from the corrected node.
-//    The committed sequence is exactly the sequential loop.
+//    iteration k0+j against a SNAPSHOT of the tree (n0 nodes at the window start): the nearest
+//    scan (the warp stages the tree through shared memory once per window), steer, clearance rays,
+//    re-drive and edge raster.  The window is then committed in iteration order; every inserted
+//    node is broadcast so that later lanes can correct their snapshot winner (new nodes have
+//    higher indices, so the snapshot winner keeps ties) and their two `in G` flags.  Only when a
+//    node of the window is strictly nearer (2.9% of the cfg-3 iterations) is the iteration
+//    expanded again, from that node, by its own lane.  The committed sequence is exactly the
+//    sequential loop.  One persistent kernel, groups pull queries from a counter.
+//
+//  * phase-split (schedule 2, experimental, trrt_wave.cuh): the same window as separate scan /
+//    expand / re-expand / commit kernels over all queries.
 #pragma once
 #include "trrt_bike.cuh"
 #include "trrt_lane.cuh"
@@ -88,7 +90,7 @@ struct Expand {
     double usteer, iccx, iccy, rad, udist; // u as stored in cameFrom
     int code;                            // TRRT_IT_STEER_CONSTRAINT / TRRT_IT_ARC_BLOCKED / EX_ACCEPT
     int flags;                           // bit0 straight, bit1 reference raises (Q7), bit2 goal reached,
-                                         // bits 4-5 number of LOS calls, bit 6/7 their results, bit 8 arc deferred
+                                         // bits 4-5 number of LOS calls, bit 6/7 their results
     int lospx, arcpx, arcang;            // counters of this iteration
     int drive;
 };
@@ -382,10 +384,6 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
 //   than lane j's snapshot winner (new nodes have higher indices, so ties stay with the snapshot), lane j alone
 //   re-expands its iteration from that node before committing.
 // ---------------------------------------------------------------------------
-#ifndef TRRT_SPEC_MIN_BLOCKS
-#define TRRT_SPEC_MIN_BLOCKS 4
-#endif
-
 #ifndef TRRT_SCAN_AHEAD
 #define TRRT_SCAN_AHEAD 1024
 #endif
