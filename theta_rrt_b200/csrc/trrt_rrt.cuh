@@ -594,16 +594,24 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         g.sync();
         // ---------------- phase B: commit in iteration order
         bool running = true;
+        // what a step needs from its lane travels in ONE word (the commit loop is a serial chain of shuffles):
+        // pre (2 bits) | qrand in tree | a node of the window is nearer | outcome (2 bits) | flags << 8
+        auto pack_static = [&]() {
+            const int p2 = (pre == -1) ? 0 : (pre == TRRT_IT_QRAND_BLOCKED ? 1 : 2);
+            const int oc = (e.code == EX_ACCEPT) ? 0 : (e.code == TRRT_IT_ARC_BLOCKED ? 1 : (e.code == TRRT_IT_STEER_CONSTRAINT ? 2 : 3));
+            return p2 | (oc << 4) | (e.flags << 8);
+        };
+        int word0 = pack_static();
         for (int j = 0; j < G; j++) {
             const int it = k0 + j;
-            const int pre_j = g.bcast(pre, j);
-            if (pre_j == TRRT_IT_NOT_RUN) break;
-            int code = pre_j, near_j = -1, newi = -1;
+            int wj = g.bcast(word0 | ((int)q_in_tree << 2) | ((int)(wbest < bd) << 3), j);
+            if ((wj & 3) == 2) break; // TRRT_IT_NOT_RUN: beyond the last iteration
+            int code = ((wj & 3) == 1) ? (int)TRRT_IT_QRAND_BLOCKED : -1, near_j = -1, newi = -1;
             bool go = true;
-            if (pre_j != TRRT_IT_QRAND_BLOCKED) {
-                if (g.bcast((int)q_in_tree, j)) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
+            if ((wj & 3) == 0) {
+                if (wj & 4) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
                 else {
-                    if (g.bcast((int)(wbest < bd), j)) {
+                    if (wj & 8) {
                         // a node of this window is strictly nearer: lane j redoes its iteration from it
                         g.sync(); // nodes written by earlier steps are visible to lane j
                         if (g.gl == j) {
@@ -611,13 +619,15 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                             expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
                             exist = -1;
                             if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
+                            word0 = pack_static();
                         }
+                        wj = g.bcast(word0, j);
                     }
                     near_j = g.bcast(near, j);
-                    const int ecode = g.bcast(e.code, j), eflags = g.bcast(e.flags, j);
+                    const int oc = (wj >> 4) & 3, eflags = wj >> 8;
                     const bool mine = g.gl == j;
                     if (a.counters) { c.scan += (unsigned long long)n; if (mine) c.steer++; }
-                    if (ecode == TRRT_IT_STEER_CONSTRAINT) code = TRRT_IT_STEER_CONSTRAINT;
+                    if (oc == 2) code = TRRT_IT_STEER_CONSTRAINT;
                     else {
                         const int nl = (eflags >> 4) & 3;
                         if (mine) {
@@ -629,7 +639,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                         }
                         nlos += nl;
                         if (eflags & 2) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; code = TRRT_IT_NOT_RUN; go = false; }
-                        else if (ecode == TRRT_IT_ARC_BLOCKED) code = TRRT_IT_ARC_BLOCKED;
+                        else if (oc == 1) code = TRRT_IT_ARC_BLOCKED;
                         else { // rrt.py:179-201
                             int idx = g.bcast(exist, j);
                             if (idx < 0) {
