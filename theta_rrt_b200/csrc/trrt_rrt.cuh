@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         // ---------------- phase B: commit in iteration order
         bool running = true;
         // what a step needs from its lane travels in ONE word (the commit loop is a serial chain of shuffles):
-        // pre (2 bits) | qrand in tree | a node of the window is nearer | outcome (2 bits) | flags << 8
+        // pre (2 bits) | qrand in tree | a node of the window is nearer | outcome (2 bits) | qnew in tree | flags << 8
         auto pack_static = [&]() {
             const int p2 = (pre == -1) ? 0 : (pre == TRRT_IT_QRAND_BLOCKED ? 1 : 2);
             const int oc = (e.code == EX_ACCEPT) ? 0 : (e.code == TRRT_IT_ARC_BLOCKED ? 1 : (e.code == TRRT_IT_STEER_CONSTRAINT ? 2 : 3));
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         int word0 = pack_static();
         for (int j = 0; j < G; j++) {
             const int it = k0 + j;
-            int wj = g.bcast(word0 | ((int)q_in_tree << 2) | ((int)(wbest < bd) << 3), j);
+            int wj = g.bcast(word0 | ((int)q_in_tree << 2) | ((int)(wbest < bd) << 3) | ((int)(exist >= 0) << 6), j);
             if ((wj & 3) == 2) break; // TRRT_IT_NOT_RUN: beyond the last iteration
             int code = ((wj & 3) == 1) ? (int)TRRT_IT_QRAND_BLOCKED : -1, near_j = -1, newi = -1;
             bool go = true;
@@ -621,9 +621,9 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                             if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
                             word0 = pack_static();
                         }
-                        wj = g.bcast(word0, j);
+                        wj = g.bcast(word0 | ((int)(exist >= 0) << 6), j);
                     }
-                    near_j = g.bcast(near, j);
+                    near_j = near; // only lane j itself uses it (its own edge record and log entry)
                     const int oc = (wj >> 4) & 3, eflags = wj >> 8;
                     const bool mine = g.gl == j;
                     if (a.counters) { c.scan += (unsigned long long)n; if (mine) c.steer++; }
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                         if (eflags & 2) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; code = TRRT_IT_NOT_RUN; go = false; }
                         else if (oc == 1) code = TRRT_IT_ARC_BLOCKED;
                         else { // rrt.py:179-201
-                            int idx = g.bcast(exist, j);
+                            int idx = (wj & 64) ? g.bcast(exist, j) : -1; // `qnew in G` (rare): the node it equals
                             if (idx < 0) {
                                 if (n >= K) { status = TRRT_ERR_CAPACITY; code = TRRT_IT_NOT_RUN; go = false; }
                                 else {
