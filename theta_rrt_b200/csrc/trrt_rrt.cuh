@@ -449,7 +449,10 @@ __device__ __forceinline__ void nearest_private(const double *__restrict__ nx, c
 // long-scoreboard stalls sit on those loads, and the CTA barrier then waits for the slowest scan).  Here the warp
 // copies the tree tile by tile with cp.async (LDGSTS, 512 coalesced bytes per instruction), two tiles in flight, and
 // all lanes read the tile from shared memory (conflict-free broadcast) while the next one is landing.
-#define TRRT_TILE_PAIRS 64 /* double2 pairs of x (and of y) per tile = 128 nodes; 2 tiles x 2 arrays x 1 KB per warp */
+#ifndef TRRT_TILE_PAIRS
+#define TRRT_TILE_PAIRS 32 /* double2 pairs of x (and of y) per tile = 64 nodes (one copy instruction per lane and array); 2 tiles x 2 arrays
+                             x 512 B per warp.  Multiple of 32.  Measured (cfg 3): 32 -> 63.7 ms, 64 -> 65.6 ms (less shared memory, more L1) */
+#endif
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -516,7 +519,7 @@ __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE
 #define TRRT_SPEC_LOCKSTEP 1
 #endif
 #ifndef TRRT_SPEC_THREADS
-#define TRRT_SPEC_THREADS 384 /* measured on B200 (cfg 3, final kernel): 384 x 2 68.6 ms, 256 x 3 70.2 ms, 256 x 4 73.8 ms; see profiles/r1/NOTES.md */
+#define TRRT_SPEC_THREADS 384 /* measured on B200 (cfg 3, final kernel): 384 x 2 63.7 ms, 768 x 1 63.7 ms, 512 x 1 67.3 ms; see profiles/r1/NOTES.md */
 #endif
 #ifndef TRRT_SPEC_BLOCKS_PER_SM
 #define TRRT_SPEC_BLOCKS_PER_SM 2
