@@ -919,10 +919,6 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
         if (per_sm < 1) per_sm = 1;
-        if (const char *cap = getenv("TRRT_MAX_BLOCKS_PER_SM")) { // experiments only
-            int c = atoi(cap);
-            if (c >= 1 && c < per_sm) per_sm = c;
-        }
         int64_t resident = (int64_t)sm_count() * per_sm; // one full wave; groups loop over the queries
         if (blocks > resident) blocks = resident;
         RrtDev *dp = &d;
@@ -1009,7 +1005,6 @@ static void theta_plan(trrt_theta_args *A, int *G) {
     if (A->n_slots <= 0) {
         // 16 warps per SM; 24 when the batch has more queries than that (measured on map2: 8192 queries 137 ms vs 152 ms)
         int wps = (A->n_queries * g > (int64_t)sm_count() * 16 * 32) ? 24 : 16;
-        if (const char *e = getenv("TRRT_THETA_WARPS_PER_SM")) wps = atoi(e); // experiments only
         int64_t resident = (int64_t)sm_count() * wps * 32 / g;
         A->n_slots = (int32_t)(A->n_queries < resident ? (A->n_queries > 0 ? A->n_queries : 1) : resident);
     }
