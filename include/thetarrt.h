@@ -107,6 +107,26 @@ int trrt_los_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
                    int64_t n, uint8_t *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * K4b los_batch_tiled.  Same contract and results as trrt_los_batch
+ * (search.lineofsight, search.py:35-94), over a second copy of the grid laid
+ * out so that the 8 pixels of a ray inside one aligned block of 8 along its
+ * driving axis come from ONE 16-byte load, for rays of any direction.
+ * Layout per map, tp = (side+7)/8: [orientation 2][K tp+1][c tp] entries of
+ * 16 bytes; in orientation 0 (rays driven by x, plotLineLow search.py:58-75)
+ * byte j bit i of entry (K, c) is pixel (x = 8c+i, y = 8K-8+j), in
+ * orientation 1 (driven by y, plotLineHigh search.py:77-94) pixel
+ * (x = 8K-8+j, y = 8c+i); 1 = free, outside the image 0.  Entries overlap by
+ * half so that the 8x8 window a block can touch is always inside one entry.
+ * trrt_tile_grid derives the copy from the packed rows of trrt_pack_grid;
+ * d_tiles must be 16-byte aligned.  Lanes take the next segment as soon as
+ * theirs is decided, so long and short rays can be mixed freely.
+ * ------------------------------------------------------------------------- */
+size_t trrt_tile_words(int H, int W); /* uint64 words per map = 4 * (tp+1) * tp */
+int trrt_tile_grid(const uint32_t *d_bits, int n_maps, int H, int W, uint64_t *d_tiles, void *stream);
+int trrt_los_batch_tiled(const uint64_t *d_tiles, int n_maps, int H, int W, const int32_t *d_map_id, const int32_t *d_seg,
+                         int64_t n, uint8_t *d_out, void *stream);
+
+/* ---------------------------------------------------------------------------
  * K1 nearest_batch.  Replaces the nearest-node scan of rrt.py:156-158
  * (np.argmin over search.L2norm, search.py:13-15): for each integer query
  * point, the index of the tree node with the smallest fp64 squared distance,

@@ -1,4 +1,5 @@
-"""LOS microbenchmark on the cfg-4 grid (8192^2, 2^20 random rays): python profiles/tools/mb_los.py"""
+"""LOS microbenchmark on the cfg-4 grid (8192^2, 2^20 random rays): python profiles/tools/mb_los.py
+Rows layout (one thread per ray / G lanes per ray) against the tiled layout with per-lane refill."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -11,15 +12,34 @@ seg = bench.make_segments(big, 1 << 20, 7)
 d_seg = torch.from_numpy(seg).to(dev)
 out = torch.empty(len(seg), dtype=torch.uint8, device=dev)
 ref = None
-for lanes in (1, 2, 4, 8, 16, 32):
-    os.environ["TRRT_LOS_LANES"] = str(lanes)
-    for _ in range(3): pl.los(d_seg, out=out)
+
+
+def run(label, **kw):
+    global ref
+    for _ in range(3): pl.los(d_seg, out=out, **kw)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(20): pl.los(d_seg, out=out)
+    for _ in range(20): pl.los(d_seg, out=out, **kw)
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 20
     res = out.cpu().numpy()
     if ref is None: ref = res.copy()
-    print(f"lanes {lanes:2d}: {ms*1e3:8.1f} us  {len(seg)/ms/1e6:8.2f} G checks/s  same as lanes=1: {bool((res == ref).all())}", flush=True)
+    print(f"{label}: {ms*1e3:8.1f} us  {len(seg)/ms/1e6:8.2f} G checks/s  same as first: {bool((res == ref).all())}", flush=True)
+
+
+for lanes in (1, 16):
+    os.environ["TRRT_LOS_LANES"] = str(lanes)
+    run(f"rows  lanes {lanes:2d}", layout="rows")
+run("tiles default", layout="tiles")
+for rpw in (32, 64, 128, 256, 512, 1024):
+    for refill in (1, 4, 8, 16, 32):
+        os.environ["TRRT_LOS_RPW"] = str(rpw); os.environ["TRRT_LOS_REFILL"] = str(refill)
+        run(f"tiles rpw {rpw:4d} refill {refill:2d}", layout="tiles")
+os.environ.pop("TRRT_LOS_RPW"); os.environ.pop("TRRT_LOS_REFILL")
+# sorted by length (what a caller could do for the rows kernel): upper bound on what refill can recover
+px = np.maximum(np.abs(seg[:, 2] - seg[:, 0]), np.abs(seg[:, 3] - seg[:, 1]))
+d_seg = torch.from_numpy(np.ascontiguousarray(seg[np.argsort(px)])).to(dev); ref = None
+os.environ["TRRT_LOS_LANES"] = "1"
+run("rows  lanes 1, rays sorted by length", layout="rows")
+run("tiles default, rays sorted by length", layout="tiles")

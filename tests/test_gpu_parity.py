@@ -42,20 +42,54 @@ def test_los_golden(maps):
         assert np.array_equal(out, z[name + "_los"]), name
 
 
+@pytest.mark.parametrize("layout", ["tiles", "rows"])
 @pytest.mark.parametrize("n,seed", [(64, 1), (257, 2), (1000, 3)])
-def test_los_vs_oracle_random(O, n, seed):
+def test_los_vs_oracle_random(O, n, seed, layout):
     free = util.synthetic_map(n, 0.12, 4, seed)
     rng = np.random.default_rng(seed)
     seg = rng.integers(-5, n + 5, size=(20000, 4)).astype(np.int32)
     seg[:2000, 2:] = seg[:2000, :2] + rng.integers(-40, 41, size=(2000, 2))
     seg[2000:2100, 2:] = seg[2000:2100, :2]  # zero length
     p = planner_for(free)
-    got = p.los(seg).cpu().numpy().astype(bool)
+    got = p.los(seg, layout=layout).cpu().numpy().astype(bool)
     ref = O.lineofsight_batch(free, seg, threads=4)
     assert np.array_equal(got, ref)
     # symmetry of the canonicalised Bresenham (search.py:47-56)
     rev = seg[:, [2, 3, 0, 1]].copy()
-    assert np.array_equal(p.los(rev).cpu().numpy().astype(bool), got)
+    assert np.array_equal(p.los(rev, layout=layout).cpu().numpy().astype(bool), got)
+
+
+def test_tile_grid_layout():
+    """trrt_tile_grid (include/thetarrt.h K4b): entry [o][K][c] holds, in byte j bit i, pixel (8c+i, 8K-8+j) for
+    orientation 0 and pixel (8K-8+j, 8c+i) for orientation 1; everything outside the image is blocked."""
+    from theta_rrt_b200 import OccupancyGrid
+    for n, seed in ((100, 1), (300, 2), (257, 3), (8, 4), (1, 5)):
+        free = np.stack([util.synthetic_map(n, 0.3, 1, seed), util.synthetic_map(n, 0.5, 2, seed + 10)])
+        tp = (n + 7) // 8
+        got = OccupancyGrid(free).tiles.cpu().numpy().view(np.uint8).reshape(2, 2, tp + 1, tp, 16)
+        pad = np.zeros((2, 8 * tp + 16, 8 * tp + 16), bool)  # image at offset (8, 8)
+        pad[:, 8:8 + n, 8:8 + n] = free
+        K, c, j, i = np.meshgrid(np.arange(tp + 1), np.arange(tp), np.arange(16), np.arange(8), indexing="ij")
+        for m in range(2):
+            o0 = pad[m][8 * K + j, 8 + 8 * c + i]  # [y + 8, x + 8] with y = 8K-8+j, x = 8c+i
+            o1 = pad[m][8 + 8 * c + i, 8 * K + j]  # x = 8K-8+j, y = 8c+i
+            for o, want in ((0, o0), (1, o1)):
+                assert np.array_equal(got[m, o], np.packbits(want, axis=-1, bitorder="little")[..., 0]), (n, m, o)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 70001])
+def test_los_tiled_refill_mix(O, n):
+    """Per-lane refill: a few very long clear rays among many short blocked ones, batch sizes around the warp size."""
+    free = util.synthetic_map(1024, 0.02, 2, 11)
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 1024, size=(n, 2))
+    ln = np.where(rng.random(n) < 0.1, 900, 6)
+    d = rng.integers(-1, 2, size=(n, 2)) * ln[:, None] + rng.integers(-3, 4, size=(n, 2))
+    seg = np.concatenate([a, a + d], 1).astype(np.int32)
+    p = planner_for(free)
+    got = p.los(seg).cpu().numpy().astype(bool)
+    assert np.array_equal(got, O.lineofsight_batch(free, seg, threads=4))
+    assert np.array_equal(got, p.los(seg, layout="rows").cpu().numpy().astype(bool))
 
 
 def test_los_empty_and_multimap(O):
@@ -66,10 +100,12 @@ def test_los_empty_and_multimap(O):
     rng = np.random.default_rng(0)
     seg = rng.integers(0, 96, size=(5000, 4)).astype(np.int32)
     mid = rng.integers(0, 3, size=5000).astype(np.int32)
-    got = p.los(seg, map_id=mid).cpu().numpy().astype(bool)
-    for m in range(3):
-        sel = mid == m
-        assert np.array_equal(got[sel], O.lineofsight_batch(free[m], seg[sel]))
+    for layout in ("tiles", "rows"):
+        assert p.los(np.zeros((0, 4), np.int32), layout=layout).numel() == 0
+        got = p.los(seg, map_id=mid, layout=layout).cpu().numpy().astype(bool)
+        for m in range(3):
+            sel = mid == m
+            assert np.array_equal(got[sel], O.lineofsight_batch(free[m], seg[sel]))
 
 
 # ------------------------------------------------------------------ nearest
@@ -492,6 +528,7 @@ def test_cfg4_full_size_nearest_and_raycast(O):
     sub = rng.integers(0, len(seg), 10000)
     assert np.array_equal(got[sub], O.lineofsight_batch(big, seg[sub], threads=4))
     assert np.array_equal(p.los(seg[:, [2, 3, 0, 1]].copy()).cpu().numpy().astype(bool), got)
+    assert np.array_equal(p.los(seg, layout="rows").cpu().numpy().astype(bool), got)  # both grid layouts agree on all 2^20
     # a ray is clear iff both halves are clear when split at a pixel of the SAME raster: endpoints free is necessary
     free_end = big[seg[:, 1], seg[:, 0]] & big[seg[:, 3], seg[:, 2]]
     assert not (got & ~free_end).any()

@@ -71,6 +71,10 @@ SIGNATURES = {
     "trrt_pack_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "trrt_los_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_void_p]),
+    "trrt_tile_words": (C.c_size_t, [C.c_int, C.c_int]),
+    "trrt_tile_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "trrt_los_batch_tiled": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_void_p]),
     "trrt_nearest_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "trrt_nearest_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

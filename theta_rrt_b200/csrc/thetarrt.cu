@@ -4,6 +4,7 @@
 //   pack_grid_kernel      byte image -> bit-packed occupancy grid
 //   los_batch_kernel      K4: search.lineofsight for independent segments, one thread per ray
 //   los_group_kernel<G>       same, G lanes per ray (optional)
+//   tile_grid_kernel / los_tiled_kernel  K4b: the same test, 8 pixels per step over 8x16-pixel strips, per-lane refill (trrt_los.cuh)
 //   nearest_tile_kernel   K1: fp64 argmin over SoA tree; query sets in registers, node slices per warp
 //   nearest_final_kernel      cross-slice reduction with lowest-index ties
 //   rrt_kernel_spec<G>    K2: fused rrt.rrt loop, speculative window of G iterations, persistent (trrt_rrt.cuh)
@@ -25,6 +26,7 @@
 #include "../../include/thetarrt.h"
 #include "trrt_bike.cuh"
 #include "trrt_device.cuh"
+#include "trrt_los.cuh"
 #include "trrt_rrt.cuh"
 #include "trrt_wave.cuh"
 
@@ -769,6 +771,47 @@ int trrt_los_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
     case 32: los_group_kernel<32><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
     default: los_batch_kernel<<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break; // one thread per segment
     }
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+size_t trrt_tile_words(int H, int W) {
+    const size_t tp = (size_t)((W > H ? W : H) + 7) / 8;
+    return 4 * (tp + 1) * tp; // 2 orientations x (tp+1)*tp entries x 2 uint64
+}
+
+int trrt_tile_grid(const uint32_t *d_bits, int n_maps, int H, int W, uint64_t *d_tiles, void *stream) {
+    int e = check_map(n_maps, H, W);
+    if (e) return e;
+    if (!d_bits || !d_tiles || ((uintptr_t)d_tiles & 15) != 0) return TRRT_ERR_INVALID_ARGUMENT;
+    const int wpr = (W + 31) / 32, tp = (W + 7) / 8;
+    size_t total = (size_t)n_maps * 2 * (tp + 1) * tp;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    tile_grid_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_bits, n_maps, H, wpr, tp, (uint4 *)d_tiles);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+int trrt_los_batch_tiled(const uint64_t *d_tiles, int n_maps, int H, int W, const int32_t *d_map_id, const int32_t *d_seg,
+                         int64_t n, uint8_t *d_out, void *stream) {
+    int e = check_map(n_maps, H, W);
+    if (e) return e;
+    if (n < 0 || !d_tiles || (n > 0 && (!d_seg || !d_out))) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TRRT_OK;
+    if (((uintptr_t)d_seg & 15) != 0 || ((uintptr_t)d_tiles & 15) != 0) return TRRT_ERR_INVALID_ARGUMENT;
+    // A warp owns `rpw` consecutive segments (a multiple of 32) and refills idle lanes from them: enough per warp to
+    // even out ray lengths, few enough that the grid still fills every SM (32 warps per SM when n allows it).
+    int rpw = 256, refill_min = 8;
+    const long long target_warps = (long long)sm_count() * 32;
+    if (n < target_warps * rpw) rpw = (int)(((n + target_warps - 1) / target_warps + 31) / 32 * 32);
+    if (const char *v = getenv("TRRT_LOS_RPW")) rpw = atoi(v);       // experiments only
+    if (const char *v = getenv("TRRT_LOS_REFILL")) refill_min = atoi(v); // experiments only
+    if (rpw < 32) rpw = 32;
+    const long long warps = (n + rpw - 1) / rpw;
+    const unsigned blocks = (unsigned)((warps + TRRT_LOS_WARPS - 1) / TRRT_LOS_WARPS);
+    los_tiled_kernel<<<blocks, TRRT_LOS_WARPS * 32, 0, (cudaStream_t)stream>>>((const uint4 *)d_tiles, H, (W + 7) / 8, d_map_id, (const int4 *)d_seg,
+                                                                               (long long)n, rpw, refill_min, d_out);
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }

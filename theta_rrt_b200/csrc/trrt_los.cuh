@@ -1,0 +1,149 @@
+// trrt_los.cuh -- K4b: search.lineofsight (search.py:35-94) for independent segments over a STRIP copy of the
+// occupancy grid, eight pixels of a ray per step, lanes picking up the next segment as soon as theirs is decided.
+//
+// Why a second layout.  In the row-major grid a 32-byte sector is 256 pixels of ONE row, so every pixel of a steep
+// ray is a new sector and a new load (the one-thread-per-ray kernel sat at 62 % of the L1 sector throughput with 53
+// sectors per ray).  Bresenham advances the driving axis by one per pixel and the other axis by at most one, so the
+// eight pixels whose driving coordinate lies in one aligned block of 8 stay inside an 8 x 8 window in the direction of
+// travel.  The strip copy stores, for every aligned block of 8 along the driving axis and every aligned offset 8K-8 on
+// the other axis, the 8 x 16 pixels [8c, 8c+8) x [8K-8, 8K+8) as one 16-byte entry (byte j = the 8 pixels at offset
+// 8K-8+j, bit i = driving coordinate 8c+i, 1 = free, outside the image 0).  Entries overlap by half, so the window of
+// any block is inside ONE entry: one 16-byte load per lane and 8 pixels.  There are two orientations: 0 for rays
+// driven by x (plotLineLow, search.py:58-75), 1 for rays driven by y (plotLineHigh, search.py:77-94), which is the
+// same layout of the transposed image.  Per map: 2 * (tp+1) * tp entries, tp = ceil(side / 8) (4x the packed rows).
+//
+// A step of a lane (uniform control flow, no per-pixel branches):
+//   1. load the entry of the block from (block index, other-axis coordinate at the block's first pixel);
+//   2. run the literal running-error recurrence of the reference for the 8 pixels (D > 0 -> step, D -= 2*dmaj;
+//      D += 2*dmin) and record the window row of each pixel as a nibble of a PRMT selector;
+//   3. shift the window to the entry's byte offset (funnel shift), gather the 8 rows with two PRMTs, and pick bit k of
+//      row k with the diagonal masks 0x08040201 / 0x80402010 restricted to the pixels that belong to the segment.
+// The first block starts at the aligned coordinate below the segment's first pixel: the recurrence is started at
+// D0 - klo*2*dmin, which is <= 0 until the first real pixel (no steps) and equals the reference's D0 there.
+//
+// Why refill.  Rays differ wildly in length and 88 % of the cfg-4 rays are blocked after a few pixels; with one
+// ray per thread a warp ran at 8 active lanes per instruction.  Here a warp owns a contiguous range of segments and
+// hands the next ones to its idle lanes (ballot + prefix popcount) whenever at least `refill_min` lanes are idle.
+//
+// The result is the AND over the ray's pixels, so grouping the tests by blocks cannot change it; the pixel sequence
+// is exactly the reference's after the canonicalisation of search.py:47-56.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace trrt {
+
+// byte of packed row y holding pixels x = 8*xb .. 8*xb+7 (0 outside the image; padding bits of the rows are 0)
+__device__ __forceinline__ unsigned strip_row_byte(const uint32_t *__restrict__ bits, int side, int wpr, int tp, int y, int xb) {
+    if (y < 0 || y >= side || xb < 0 || xb >= tp) return 0u;
+    return (__ldg(bits + (size_t)y * wpr + (xb >> 2)) >> ((xb & 3) * 8)) & 0xffu;
+}
+
+// bit-packed rows -> strip entries of both orientations; one thread per entry
+__global__ void tile_grid_kernel(const uint32_t *__restrict__ bits, int n_maps, int side, int wpr, int tp, uint4 *__restrict__ tiles) {
+    const size_t epo = (size_t)(tp + 1) * tp, total = epo * 2 * n_maps;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t m = e / (2 * epo), r = e - m * 2 * epo;
+        const int orient = r >= epo, K = (int)((r - (orient ? epo : 0)) / tp), c = (int)((r - (orient ? epo : 0)) - (size_t)K * tp);
+        const uint32_t *src = bits + m * (size_t)side * wpr;
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+        if (!orient) {
+            // driving axis x: byte j = pixels (8c .. 8c+7, y = 8K-8+j)
+#pragma unroll
+            for (int j = 0; j < 16; j++) w[j >> 2] |= strip_row_byte(src, side, wpr, tp, 8 * K - 8 + j, c) << ((j & 3) * 8);
+        } else {
+            // driving axis y: byte j = pixels (x = 8K-8+j, 8c .. 8c+7): transpose 8 rows of 16 pixels
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int y = 8 * c + i;
+                const unsigned v = strip_row_byte(src, side, wpr, tp, y, K - 1) | (strip_row_byte(src, side, wpr, tp, y, K) << 8);
+#pragma unroll
+                for (int j = 0; j < 16; j++) w[j >> 2] |= ((v >> j) & 1u) << ((j & 3) * 8 + i);
+            }
+        }
+        tiles[e] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+#define TRRT_LOS_WARPS 4
+__global__ void __launch_bounds__(TRRT_LOS_WARPS * 32) los_tiled_kernel(const uint4 *__restrict__ tiles, int side, int tp, const int32_t *__restrict__ map_id,
+                                                                        const int4 *__restrict__ seg, long long n, int rays_per_warp, int refill_min,
+                                                                        uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    long long next = warp * rays_per_warp; // warp-uniform: first segment not yet handed to a lane
+    if (next >= n) return;
+    const long long end = (next + rays_per_warp < n) ? next + rays_per_warp : n;
+    const size_t epo = (size_t)(tp + 1) * tp;
+
+    bool active = false, neg = false;
+    long long idx = 0;
+    const uint4 *gt = tiles;
+    int a = 0, aend = 0, b = 0, D = 0, dmaj2 = 0, dmin2 = 0, klo = 0;
+
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        if (next < end && (need == 0xffffffffu || __popc(need) >= refill_min)) {
+            if (!active) {
+                const long long i = next + __popc(need & lt);
+                if (i < end) {
+                    const int4 s = __ldg(seg + i);
+                    // search.valid on both endpoints (search.py:17-24, :36); maps are square
+                    if ((unsigned)s.x < (unsigned)side && (unsigned)s.y < (unsigned)side && (unsigned)s.z < (unsigned)side &&
+                        (unsigned)s.w < (unsigned)side) {
+                        const bool low = abs(s.w - s.y) < abs(s.z - s.x); // search.py:47
+                        int p0 = low ? s.x : s.y, q0 = low ? s.y : s.x, p1 = low ? s.z : s.w, q1 = low ? s.w : s.z;
+                        if (p0 > p1) { int t = p0; p0 = p1; p1 = t; t = q0; q0 = q1; q1 = t; } // search.py:48-56
+                        const int dmaj = p1 - p0, dq = q1 - q0;
+                        neg = dq < 0;
+                        dmaj2 = 2 * dmaj; dmin2 = 2 * abs(dq);
+                        klo = p0 & 7; a = p0 & ~7; aend = p1; b = q0;
+                        D = dmin2 - dmaj - klo * dmin2; // search.py:66 / :85, moved back to the block's first slot
+                        gt = tiles + (map_id ? (size_t)__ldg(map_id + i) * 2 * epo : 0) + (low ? 0 : epo);
+                        idx = i;
+                        active = true;
+                    } else {
+                        out[i] = 0;
+                    }
+                }
+            }
+            next += __popc(need);
+        } else if (need == 0xffffffffu) {
+            break;
+        }
+        if (active) {
+            const uint4 wv = __ldg(gt + (size_t)((b >> 3) + (neg ? 0 : 1)) * tp + (a >> 3));
+            const int sb = (b & 7) + (neg ? 1 : 0); // byte of the entry where the window starts
+            unsigned sel = 0;
+            int j = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                sel |= (unsigned)j << (4 * k);
+                const bool st = D > 0;
+                j += st ? 1 : 0;
+                D += st ? dmin2 - dmaj2 : dmin2;
+            }
+            b += neg ? -j : j;
+            const int q = sb >> 2, sh = (sb & 3) * 8;
+            const unsigned r0 = q == 0 ? wv.x : q == 1 ? wv.y : wv.z;
+            const unsigned r1 = q == 0 ? wv.y : q == 1 ? wv.z : wv.w;
+            const unsigned r2 = q == 0 ? wv.z : wv.w; // unused when q == 2 (sh == 0)
+            const unsigned ulo = __funnelshift_r(r0, r1, sh), uhi = __funnelshift_r(r1, r2, sh);
+            if (neg) sel ^= 0x77777777u; // travel towards smaller coordinates: row j is byte 7 - j
+            const unsigned rows_lo = __byte_perm(ulo, uhi, sel & 0xffffu), rows_hi = __byte_perm(ulo, uhi, sel >> 16);
+            const int left = aend - a, khi = left < 7 ? left : 7;
+            const unsigned kmask = ((2u << khi) - 1u) & ~((1u << klo) - 1u);
+            const unsigned rep = kmask * 0x01010101u;
+            const unsigned bad = (~rows_lo & rep & 0x08040201u) | (~rows_hi & rep & 0x80402010u);
+            a += 8;
+            klo = 0;
+            if (bad != 0u || a > aend) {
+                out[idx] = bad ? 0 : 1;
+                active = false;
+            }
+        }
+    }
+}
+
+} // namespace trrt

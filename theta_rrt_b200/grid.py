@@ -2,7 +2,8 @@
 
 Layout (include/thetarrt.h): per map H rows of wpr=(W+31)//32 32-bit words,
 pixel (x, y) = bit (x & 31) of word [y*wpr + (x >> 5)], 1 = free, padding = blocked.
-Packing runs on the device (trrt_pack_grid).
+Packing runs on the device (trrt_pack_grid).  `tiles` is a derived copy in overlapping 8x16-pixel strips, one set
+per driving axis, for the batched line-of-sight kernel (trrt_tile_grid; layout in include/thetarrt.h, K4b).
 """
 from __future__ import annotations
 
@@ -43,6 +44,21 @@ class OccupancyGrid:
                        "trrt_pack_grid")
             torch.cuda.current_stream(self.device).synchronize()  # d_free may be freed after return
         self.nbytes = words * 4
+        self._tiles = None
+
+    @property
+    def tiles(self):
+        """Strip copy of the grid (include/thetarrt.h K4b, 4x the packed rows), built on first use by trrt_tile_grid
+        from the packed rows."""
+        if self._tiles is None:
+            lib = _lib.load()
+            with torch.cuda.device(self.device):
+                t = torch.empty(self.n_maps * lib.trrt_tile_words(self.H, self.W), dtype=torch.int64, device=self.device)
+                st = torch.cuda.current_stream(self.device).cuda_stream
+                _lib.check(lib.trrt_tile_grid(self.bits.data_ptr(), self.n_maps, self.H, self.W, t.data_ptr(), st),
+                           "trrt_tile_grid")
+            self._tiles = t
+        return self._tiles
 
     @property
     def shape(self):

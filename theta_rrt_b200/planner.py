@@ -121,8 +121,12 @@ class Planner:
         return t
 
     # ------------------------------------------------------------------ K4
-    def los(self, seg, map_id=None, out=None):
-        """search.lineofsight for segments int32 [n,4] = (x0,y0,x1,y1).  Returns uint8 [n] (1 = visible)."""
+    def los(self, seg, map_id=None, out=None, layout="tiles"):
+        """search.lineofsight for segments int32 [n,4] = (x0,y0,x1,y1).  Returns uint8 [n] (1 = visible).
+        layout "tiles" (default) tests 8 pixels per step on the strip copy of the grid with per-lane refill (trrt_los_batch_tiled),
+        "rows" the packed rows with one thread per ray (trrt_los_batch); the results are identical."""
+        if layout not in ("tiles", "rows"):
+            raise ValueError("layout must be 'tiles' or 'rows'")
         with torch.cuda.device(self.device):
             seg = self._dev(seg, torch.int32).reshape(-1, 4)
             n = seg.shape[0]
@@ -130,9 +134,14 @@ class Planner:
             if out is None:
                 out = torch.empty(n, dtype=torch.uint8, device=self.device)
             g = self.grid
-            _lib.check(self.lib.trrt_los_batch(g.bits.data_ptr(), g.n_maps, g.H, g.W,
-                                               mid.data_ptr() if mid is not None else None, seg.data_ptr(), n,
-                                               out.data_ptr(), self._stream()), "trrt_los_batch")
+            if layout == "tiles":
+                _lib.check(self.lib.trrt_los_batch_tiled(g.tiles.data_ptr(), g.n_maps, g.H, g.W,
+                                                         mid.data_ptr() if mid is not None else None, seg.data_ptr(),
+                                                         n, out.data_ptr(), self._stream()), "trrt_los_batch_tiled")
+            else:
+                _lib.check(self.lib.trrt_los_batch(g.bits.data_ptr(), g.n_maps, g.H, g.W,
+                                                   mid.data_ptr() if mid is not None else None, seg.data_ptr(), n,
+                                                   out.data_ptr(), self._stream()), "trrt_los_batch")
         return out
 
     # ------------------------------------------------------------------ K1
