@@ -32,11 +32,12 @@ for lanes in (1, 16):
     os.environ["TRRT_LOS_LANES"] = str(lanes)
     run(f"rows  lanes {lanes:2d}", layout="rows")
 run("tiles default", layout="tiles")
-for rpw in (32, 64, 128, 256, 512, 1024):
-    for refill in (1, 4, 8, 16, 32):
-        os.environ["TRRT_LOS_RPW"] = str(rpw); os.environ["TRRT_LOS_REFILL"] = str(refill)
-        run(f"tiles rpw {rpw:4d} refill {refill:2d}", layout="tiles")
-os.environ.pop("TRRT_LOS_RPW"); os.environ.pop("TRRT_LOS_REFILL")
+for coop in (4, 8, 16):
+    for rpw in (96, 128, 160, 192, 224, 256):
+        for refill in (6, 8, 12):
+            os.environ["TRRT_LOS_RPW"] = str(rpw); os.environ["TRRT_LOS_REFILL"] = str(refill); os.environ["TRRT_LOS_COOP"] = str(coop)
+            run(f"tiles coop {coop:2d} rpw {rpw:4d} refill {refill:2d}", layout="tiles")
+os.environ.pop("TRRT_LOS_RPW"); os.environ.pop("TRRT_LOS_REFILL"); os.environ.pop("TRRT_LOS_COOP")
 # sorted by length (what a caller could do for the rows kernel): upper bound on what refill can recover
 px = np.maximum(np.abs(seg[:, 2] - seg[:, 0]), np.abs(seg[:, 3] - seg[:, 1]))
 d_seg = torch.from_numpy(np.ascontiguousarray(seg[np.argsort(px)])).to(dev); ref = None

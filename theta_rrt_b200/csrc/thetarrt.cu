@@ -800,18 +800,27 @@ int trrt_los_batch_tiled(const uint64_t *d_tiles, int n_maps, int H, int W, cons
     if (n < 0 || !d_tiles || (n > 0 && (!d_seg || !d_out))) return TRRT_ERR_INVALID_ARGUMENT;
     if (n == 0) return TRRT_OK;
     if (((uintptr_t)d_seg & 15) != 0 || ((uintptr_t)d_tiles & 15) != 0) return TRRT_ERR_INVALID_ARGUMENT;
-    // A warp owns `rpw` consecutive segments (a multiple of 32) and refills idle lanes from them: enough per warp to
-    // even out ray lengths, few enough that the grid still fills every SM (32 warps per SM when n allows it).
-    int rpw = 256, refill_min = 8;
-    const long long target_warps = (long long)sm_count() * 32;
-    if (n < target_warps * rpw) rpw = (int)(((n + target_warps - 1) / target_warps + 31) / 32 * 32);
-    if (const char *v = getenv("TRRT_LOS_RPW")) rpw = atoi(v);       // experiments only
+    // A warp owns `rpw` consecutive segments (a multiple of 32) and refills idle lanes from them.  The kernel is bound
+    // by the integer pipes, not by latency, so long ranges (fewer refill rounds and tails) beat more resident warps:
+    // 256 segments per warp when that still gives every SM 24 warps, never fewer than 64.  Measured on the cfg-4 rays:
+    // rpw 96 .. 256 -> 73 .. 71 us; refill threshold 6 / 8 / 12 idle lanes -> 72.6 / 70.6 / 70.8 us; cooperative tail
+    // from 4 / 8 / 16 remaining rays -> 72.4 / 70.6 / 70.7 us, without it 87 us.
+    int refill_min = 8, coop_max = 8;
+    const long long target_warps = (long long)sm_count() * 24;
+    long long rpw = ((n + target_warps - 1) / target_warps + 31) / 32 * 32;
+    if (rpw < 64) rpw = 64;
+    if (rpw > 256) rpw = 256;
+    if (const char *v = getenv("TRRT_LOS_RPW")) rpw = atoi(v);           // experiments only
     if (const char *v = getenv("TRRT_LOS_REFILL")) refill_min = atoi(v); // experiments only
+    if (const char *v = getenv("TRRT_LOS_COOP")) coop_max = atoi(v);     // experiments only (0 = no cooperative tail)
     if (rpw < 32) rpw = 32;
+    if (rpw > (1 << 30)) rpw = 1 << 30;
+    if (refill_min < 1) refill_min = 1;
+    if (refill_min > 32) refill_min = 32;
     const long long warps = (n + rpw - 1) / rpw;
     const unsigned blocks = (unsigned)((warps + TRRT_LOS_WARPS - 1) / TRRT_LOS_WARPS);
     los_tiled_kernel<<<blocks, TRRT_LOS_WARPS * 32, 0, (cudaStream_t)stream>>>((const uint4 *)d_tiles, H, (W + 7) / 8, d_map_id, (const int4 *)d_seg,
-                                                                               (long long)n, rpw, refill_min, d_out);
+                                                                               (long long)n, (int)rpw, refill_min, coop_max, d_out);
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }

@@ -65,29 +65,66 @@ __global__ void tile_grid_kernel(const uint32_t *__restrict__ bits, int n_maps, 
     }
 }
 
+// One block of a ray: the 8 slots whose driving coordinate is A .. A+7 (A a multiple of 8), of which slots
+// klo .. min(7, aend - A) belong to the segment.  b, D are the other-axis coordinate and the running error at slot 0
+// and are advanced to slot 0 of the next block.  gtn = base of the orientation, moved on by one row of entries when the
+// ray travels towards larger coordinates (so that the entry index is (b >> 3) * tp + (A >> 3) either way).
+// Returns a non-zero word when one of the segment's pixels is blocked.
+__device__ __forceinline__ unsigned strip_block(const uint4 *__restrict__ gtn, int tp, int A, int aend, int klo, bool neg, int dmaj2, int dmin2,
+                                                int &b, int &D) {
+    const uint4 wv = __ldg(gtn + ((b >> 3) * tp + (A >> 3)));
+    const int sb = (b & 7) + (neg ? 1 : 0); // byte of the entry where the window starts
+    // literal recurrence of search.py:68-74 / :87-93; nibble k of sel = number of steps taken before slot k
+    unsigned sel = 0;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        if (D > 0) { sel += 0x11111110u << (4 * k); D -= dmaj2; }
+        D += dmin2;
+    }
+    int j = (int)(sel >> 28);
+    if (D > 0) { j++; D -= dmaj2; }
+    D += dmin2;
+    b += neg ? -j : j;
+    const int q = sb >> 2, sh = (sb & 3) * 8;
+    const unsigned r0 = q == 0 ? wv.x : q == 1 ? wv.y : wv.z;
+    const unsigned r1 = q == 0 ? wv.y : q == 1 ? wv.z : wv.w;
+    const unsigned r2 = q == 0 ? wv.z : wv.w; // unused when q == 2 (sh == 0)
+    const unsigned ulo = __funnelshift_r(r0, r1, sh), uhi = __funnelshift_r(r1, r2, sh);
+    if (neg) sel ^= 0x77777777u; // travel towards smaller coordinates: row j is byte 7 - j
+    const unsigned rows_lo = __byte_perm(ulo, uhi, sel & 0xffffu), rows_hi = __byte_perm(ulo, uhi, sel >> 16);
+    const int left = aend - A, khi = left < 7 ? left : 7;
+    const unsigned kmask = ((2u << khi) - 1u) & ~((1u << klo) - 1u);
+    const unsigned rep = kmask * 0x01010101u;
+    return (~rows_lo & rep & 0x08040201u) | (~rows_hi & rep & 0x80402010u);
+}
+
 #define TRRT_LOS_WARPS 4
-__global__ void __launch_bounds__(TRRT_LOS_WARPS * 32) los_tiled_kernel(const uint4 *__restrict__ tiles, int side, int tp, const int32_t *__restrict__ map_id,
-                                                                        const int4 *__restrict__ seg, long long n, int rays_per_warp, int refill_min,
-                                                                        uint8_t *__restrict__ out) {
+#define TRRT_LOS_CTAS_PER_SM 8
+__global__ void __launch_bounds__(TRRT_LOS_WARPS * 32, TRRT_LOS_CTAS_PER_SM)
+    los_tiled_kernel(const uint4 *__restrict__ tiles, int side, int tp, const int32_t *__restrict__ map_id, const int4 *__restrict__ seg, long long n,
+                     int rays_per_warp, int refill_min, int coop_max, uint8_t *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    long long next = warp * rays_per_warp; // warp-uniform: first segment not yet handed to a lane
-    if (next >= n) return;
-    const long long end = (next + rays_per_warp < n) ? next + rays_per_warp : n;
-    const size_t epo = (size_t)(tp + 1) * tp;
+    const long long begin = ((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * rays_per_warp;
+    if (begin >= n) return;
+    const int cnt = (int)((begin + rays_per_warp < n) ? rays_per_warp : n - begin); // segments of this warp
+    seg += begin;
+    out += begin;
+    if (map_id) map_id += begin;
+    const int epo = (tp + 1) * tp; // entries per orientation (< 2^25 for side <= 32768)
+    int nxt = 0;                   // warp-uniform: first segment of the range not yet handed to a lane
 
     bool active = false, neg = false;
-    long long idx = 0;
-    const uint4 *gt = tiles;
-    int a = 0, aend = 0, b = 0, D = 0, dmaj2 = 0, dmin2 = 0, klo = 0;
+    const uint4 *gtn = tiles;
+    int idx = 0, a = 0, aend = 0, b = 0, D = 0, dmaj2 = 0, dmin2 = 0, klo = 0;
 
     for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, !active);
-        if (next < end && (need == 0xffffffffu || __popc(need) >= refill_min)) {
+        unsigned act = __ballot_sync(0xffffffffu, active);
+        int na = __popc(act);
+        if (nxt < cnt && 32 - na >= refill_min) {
             if (!active) {
-                const long long i = next + __popc(need & lt);
-                if (i < end) {
+                const int i = nxt + __popc(~act & lt);
+                if (i < cnt) {
                     const int4 s = __ldg(seg + i);
                     // search.valid on both endpoints (search.py:17-24, :36); maps are square
                     if ((unsigned)s.x < (unsigned)side && (unsigned)s.y < (unsigned)side && (unsigned)s.z < (unsigned)side &&
@@ -100,7 +137,7 @@ __global__ void __launch_bounds__(TRRT_LOS_WARPS * 32) los_tiled_kernel(const ui
                         dmaj2 = 2 * dmaj; dmin2 = 2 * abs(dq);
                         klo = p0 & 7; a = p0 & ~7; aend = p1; b = q0;
                         D = dmin2 - dmaj - klo * dmin2; // search.py:66 / :85, moved back to the block's first slot
-                        gt = tiles + (map_id ? (size_t)__ldg(map_id + i) * 2 * epo : 0) + (low ? 0 : epo);
+                        gtn = tiles + ((size_t)(map_id ? __ldg(map_id + i) : 0) * 2 * epo + (low ? 0 : epo) + (neg ? 0 : tp));
                         idx = i;
                         active = true;
                     } else {
@@ -108,39 +145,70 @@ __global__ void __launch_bounds__(TRRT_LOS_WARPS * 32) los_tiled_kernel(const ui
                     }
                 }
             }
-            next += __popc(need);
-        } else if (need == 0xffffffffu) {
-            break;
+            nxt += 32 - na;
+            act = __ballot_sync(0xffffffffu, active);
+            na = __popc(act);
         }
-        if (active) {
-            const uint4 wv = __ldg(gt + (size_t)((b >> 3) + (neg ? 0 : 1)) * tp + (a >> 3));
-            const int sb = (b & 7) + (neg ? 1 : 0); // byte of the entry where the window starts
-            unsigned sel = 0;
-            int j = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                sel |= (unsigned)j << (4 * k);
-                const bool st = D > 0;
-                j += st ? 1 : 0;
-                D += st ? dmin2 - dmaj2 : dmin2;
+        if (na == 0) {
+            if (nxt >= cnt) break;
+            continue;
+        }
+        if (nxt < cnt || na > coop_max) {
+            // every lane advances its own ray by one block
+            if (active) {
+                const unsigned bad = strip_block(gtn, tp, a, aend, klo, neg, dmaj2, dmin2, b, D);
+                a += 8;
+                klo = 0;
+                if (bad != 0u || a > aend) {
+                    out[idx] = bad ? 0 : 1;
+                    active = false;
+                }
             }
-            b += neg ? -j : j;
-            const int q = sb >> 2, sh = (sb & 3) * 8;
-            const unsigned r0 = q == 0 ? wv.x : q == 1 ? wv.y : wv.z;
-            const unsigned r1 = q == 0 ? wv.y : q == 1 ? wv.z : wv.w;
-            const unsigned r2 = q == 0 ? wv.z : wv.w; // unused when q == 2 (sh == 0)
-            const unsigned ulo = __funnelshift_r(r0, r1, sh), uhi = __funnelshift_r(r1, r2, sh);
-            if (neg) sel ^= 0x77777777u; // travel towards smaller coordinates: row j is byte 7 - j
-            const unsigned rows_lo = __byte_perm(ulo, uhi, sel & 0xffffu), rows_hi = __byte_perm(ulo, uhi, sel >> 16);
-            const int left = aend - a, khi = left < 7 ? left : 7;
-            const unsigned kmask = ((2u << khi) - 1u) & ~((1u << klo) - 1u);
-            const unsigned rep = kmask * 0x01010101u;
-            const unsigned bad = (~rows_lo & rep & 0x08040201u) | (~rows_hi & rep & 0x80402010u);
-            a += 8;
-            klo = 0;
-            if (bad != 0u || a > aend) {
-                out[idx] = bad ? 0 : 1;
-                active = false;
+        } else {
+            // The warp's range is used up and few rays are left: the idle lanes join in.  The lanes are split into
+            // groups of G = 32 / nextpow2(na); group g takes the g-th remaining ray and member m its m-th next block.
+            // The state m blocks ahead follows from the invariant D in (2*dmin - 2*dmaj, 2*dmin]: D advances by
+            // 2*dmin per pixel modulo 2*dmaj, and the number of wraps is the number of steps.
+            const int lg = 32 - __clz(na - 1), G = 32 >> lg, g = lane >> (5 - lg), m = lane & (G - 1);
+            const unsigned srcu = __fns(act, 0, g + 1);
+            const bool has = srcu < 32u;
+            const int src = has ? (int)srcu : lane;
+            const int sa = __shfl_sync(0xffffffffu, a, src), saend = __shfl_sync(0xffffffffu, aend, src);
+            int sbb = __shfl_sync(0xffffffffu, b, src), sD = __shfl_sync(0xffffffffu, D, src);
+            const int sdmaj2 = __shfl_sync(0xffffffffu, dmaj2, src), sdmin2 = __shfl_sync(0xffffffffu, dmin2, src);
+            const int sklo = __shfl_sync(0xffffffffu, klo, src);
+            const bool sneg = __shfl_sync(0xffffffffu, (int)neg, src) != 0;
+            const uint4 *sgtn = (const uint4 *)__shfl_sync(0xffffffffu, (unsigned long long)gtn, src);
+            const int A = sa + 8 * m;
+            // the first block of a ray starts before the segment (D is not yet inside the invariant interval): alone
+            const bool work = has && A <= saend && (m == 0 || sklo == 0);
+            unsigned bad = 0u;
+            if (work) {
+                if (m > 0) {
+                    const int lo = sdmin2 - sdmaj2 + 1;
+                    const unsigned u = (unsigned)(sD + 8 * m * sdmin2 - lo), steps = u / (unsigned)sdmaj2; // sdmaj2 > 0: saend > sa
+                    sD = lo + (int)(u - steps * (unsigned)sdmaj2);
+                    sbb += sneg ? -(int)steps : (int)steps;
+                }
+                bad = strip_block(sgtn, tp, A, saend, m == 0 ? sklo : 0, sneg, sdmaj2, sdmin2, sbb, sD);
+            }
+            const unsigned badm = __ballot_sync(0xffffffffu, bad != 0u);
+            // back to the owners: rank r among the active lanes = group r; the ray moves on nb blocks
+            const int r = __popc(act & lt), nb = klo ? 1 : G;
+            const int from = active ? r * G + nb - 1 : lane;
+            const int nb_ = __shfl_sync(0xffffffffu, sbb, from), nD_ = __shfl_sync(0xffffffffu, sD, from);
+            if (active) {
+                const unsigned gm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (r * G);
+                const bool blocked = (badm & gm) != 0u;
+                a += 8 * nb;
+                klo = 0;
+                if (blocked || a > aend) {
+                    out[idx] = blocked ? 0 : 1;
+                    active = false;
+                } else {
+                    b = nb_;
+                    D = nD_;
+                }
             }
         }
     }

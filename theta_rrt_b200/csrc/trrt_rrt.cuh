@@ -518,6 +518,9 @@ __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE
 #ifndef TRRT_SPEC_LOCKSTEP
 #define TRRT_SPEC_LOCKSTEP 1
 #endif
+#ifndef TRRT_SPEC_PREDICT
+#define TRRT_SPEC_PREDICT 1 /* lane-parallel predicted re-expansions before the commit (phase A, part 3) */
+#endif
 #ifndef TRRT_SPEC_THREADS
 #define TRRT_SPEC_THREADS 384 /* measured on B200 (cfg 3, final kernel): 384 x 2 63.7 ms, 768 x 1 63.7 ms, 512 x 1 67.3 ms; see profiles/r1/NOTES.md */
 #endif
@@ -595,6 +598,40 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
             if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
         }
         g.sync();
+        // ---------------- phase A, part 3: predicted re-expansions, lane-parallel
+        // A lane whose nearest node will be a node of its own window has to expand again from that node.  Doing that
+        // inside the serial commit costs one full expansion per such lane (0.92 per window on cfg 3, up to 4-5), with
+        // the other 31 lanes and - through the lockstep barrier - the other warps of the CTA waiting.  The candidates are
+        // known now: assume every lane whose tentative outcome inserts a node commits exactly that node; then lane j's
+        // nearest window node is the first strict minimum over the tentative nodes of the lanes before it.  All
+        // predicted lanes expand from their predicted node together (e2); the commit verifies the assumption (the
+        // node that is really nearest was inserted by the predicted lane from its tentative outcome) and falls back to
+        // the serial expansion otherwise.
+        bool has2 = false;
+        int pred = -1, pred_idx = -2, exist2 = -1, islot2 = 0;
+        Expand e2;
+        if (G > 1 && TRRT_SPEC_PREDICT) {
+            const bool will_insert = live && e.code == EX_ACCEPT && exist < 0 && !(e.flags & 2);
+            unsigned ins = g.ballot(will_insert);
+            double pbest = bd;
+            ins &= ~(1u << (G - 1)); // nobody comes after the last lane
+            while (ins) {
+                const int i = __ffs(ins) - 1;
+                ins &= ins - 1;
+                const double vx = g.bcast(e.wx, i), vy = g.bcast(e.wy, i);
+                const double dx = qx - vx, dy = qy - vy;
+                const double d = dx * dx + dy * dy;
+                if (g.gl > i && d < pbest) { pbest = d; pred = i; }
+            }
+            has2 = live && pred >= 0;
+            const int src = has2 ? pred : g.gl;
+            const double ox = g.bcast(e.wx, src), oy = g.bcast(e.wy, src), oth = g.bcast(e.wth, src);
+            if (has2) {
+                expand_from<1>(solo, Q.m, a.P, ox, oy, oth, qx, qy, qth, Q.gx, Q.gy, Q.gth, e2);
+                if (e2.code == EX_ACCEPT) exist2 = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e2.wx, e2.wy, e2.wth, probes, islot2);
+            }
+            g.sync();
+        }
         // ---------------- phase B: commit in iteration order
         bool running = true;
         // what a step needs from its lane travels in ONE word (the commit loop is a serial chain of shuffles):
@@ -614,14 +651,20 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
             if ((wj & 3) == 0) {
                 if (wj & 4) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
                 else {
-                    if (wj & 8) {
-                        // a node of this window is strictly nearer: lane j redoes its iteration from it
-                        g.sync(); // nodes written by earlier steps are visible to lane j
+                    const bool moved = (wj & 8) != 0; // lane j does not commit its tentative outcome
+                    if (moved) {
+                        // a node of this window is strictly nearer: lane j's iteration starts from it.  Either that is
+                        // the node it was expanded from ahead of time (part 3), or lane j redoes the expansion now.
+                        const bool hit = g.bcast((int)(has2 && widx == pred_idx), j) != 0;
+                        if (!hit) g.sync(); // nodes written by earlier steps are visible to lane j
                         if (g.gl == j) {
                             near = widx;
-                            expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
-                            exist = -1;
-                            if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
+                            if (hit) { e = e2; exist = exist2; islot = islot2; }
+                            else {
+                                expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
+                                exist = -1;
+                                if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
+                            }
                             word0 = pack_static();
                         }
                         wj = g.bcast(word0 | ((int)(exist >= 0) << 6), j);
@@ -662,6 +705,10 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                                         if (d < wbest) { wbest = d; widx = idx; }
                                         if (qx == vx && qy == vy && qth == vth) q_in_tree = true;
                                         if (exist < 0 && e.wx == vx && e.wy == vy && e.wth == vth) exist = idx;
+                                        if (has2) {
+                                            if (pred == j) pred_idx = moved ? -2 : idx; // the node part 3 assumed, or another one
+                                            if (exist2 < 0 && e2.wx == vx && e2.wy == vy && e2.wth == vth) exist2 = idx;
+                                        }
                                     }
                                 }
                             } else code = TRRT_IT_EXISTING_NODE;
