@@ -728,6 +728,17 @@ const char *trrt_error_string(int err) {
 }
 const char *trrt_last_cuda_error(void) { return g_last_cuda_error; }
 
+#ifdef TRRT_PHASE_PROF
+// experiment builds only: read (and clear) the phase sums of rrt_kernel_spec; synchronises the device
+extern "C" int trrt_debug_phase_prof(unsigned long long *host_out24) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(host_out24, trrt::g_phase_prof, sizeof(unsigned long long) * 24));
+    unsigned long long z[24] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(trrt::g_phase_prof, z, sizeof(z)));
+    return TRRT_OK;
+}
+#endif
+
 void trrt_default_params(trrt_params *p) {
     p->thetastar = 1; p->forwardonly = 1; p->bikelength = 5; p->leftconstraint = -65; p->rightconstraint = 65;
     p->frontclearance = 2; p->maxdrivedist = 30; p->tol_xy = 10; p->tol_ang = 45; p->weightxy = .6;

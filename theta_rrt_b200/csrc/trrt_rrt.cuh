@@ -528,6 +528,14 @@ __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE
 #define TRRT_SPEC_BLOCKS_PER_SM 2
 #endif
 
+#ifdef TRRT_PHASE_PROF
+// experiment builds only (profiles/tools/phase_prof.py): per-warp clock64 sums of the phases of a window
+__device__ unsigned long long g_phase_prof[24];
+#define TRRT_PROF(...) __VA_ARGS__
+#else
+#define TRRT_PROF(...)
+#endif
+
 template <int G>
 __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rrt_kernel_spec(const RrtDev a) {
     const Group<G> g;
@@ -542,6 +550,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
     RrtQuery Q;
     RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0}; // scan is kept uniform; the others are lane-private sums, folded at the end
     int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND, iters = 0, k0 = 0;
+    TRRT_PROF(unsigned long long pf[24]; for (int i_ = 0; i_ < 24; i_++) pf[i_] = 0; long long t0_, t1_, t2_, t3_, t4_;)
     for (;;) {
         if (!have && !drained) {
             unsigned long long qq = 0;
@@ -557,6 +566,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
             }
         }
         // ---------------- phase A, part 1: sample, `qrand in G`, nearest scan
+        TRRT_PROF(t0_ = clock64();)
         const int n0 = n;
         int pre = TRRT_IT_NOT_RUN; // TRRT_IT_QRAND_BLOCKED, TRRT_IT_NOT_RUN (beyond the last iteration / no query) or -1 = live
         bool q_in_tree = false;    // rrt.py:151 against the snapshot (+ nodes of this window, folded in below)
@@ -587,7 +597,9 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         }
 #if TRRT_SPEC_LOCKSTEP
         // ---------------- CTA barrier: expansion code is entered together; also the exit test
+        TRRT_PROF(t1_ = clock64();)
         if (!__syncthreads_or(have ? 1 : 0)) break;
+        TRRT_PROF(t2_ = clock64(); if (have) { const unsigned long long s_ = t1_ - t0_; pf[0] += s_; pf[1] += s_ * s_ >> 10; pf[2] += t2_ - t1_; pf[10]++; })
         if (!have) continue;
 #else
         if (!have) break; // no query left for this group
@@ -598,6 +610,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
             if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
         }
         g.sync();
+        TRRT_PROF(t3_ = clock64(); { const unsigned long long s_ = t3_ - t2_; pf[3] += s_; pf[4] += s_ * s_ >> 10; })
         // ---------------- phase A, part 3: predicted re-expansions, lane-parallel
         // A lane whose nearest node will be a node of its own window has to expand again from that node.  Doing that
         // inside the serial commit costs one full expansion per such lane (0.92 per window on cfg 3, up to 4-5), with
@@ -631,7 +644,9 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                 if (e2.code == EX_ACCEPT) exist2 = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e2.wx, e2.wy, e2.wth, probes, islot2);
             }
             g.sync();
+            TRRT_PROF({ const unsigned m_ = g.ballot(has2); if (m_) { pf[11]++; pf[12] += __popc(m_); } })
         }
+        TRRT_PROF(t4_ = clock64(); { const unsigned long long s_ = t4_ - t3_; pf[5] += s_; pf[6] += s_ * s_ >> 10; })
         // ---------------- phase B: commit in iteration order
         bool running = true;
         // what a step needs from its lane travels in ONE word (the commit loop is a serial chain of shuffles):
@@ -656,15 +671,24 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                         // a node of this window is strictly nearer: lane j's iteration starts from it.  Either that is
                         // the node it was expanded from ahead of time (part 3), or lane j redoes the expansion now.
                         const bool hit = g.bcast((int)(has2 && widx == pred_idx), j) != 0;
-                        if (!hit) g.sync(); // nodes written by earlier steps are visible to lane j
+                        if (!hit) {
+                            // Not foreseen (typically: the node comes from a lane that itself moved).  The nodes of the
+                            // steps before j are final, so every lane from j on whose nearest node so far is one of
+                            // them, and which holds no expansion from it, expands now, together with lane j; lanes still
+                            // waiting for the node of a later lane (pred > j) keep their prediction.
+                            g.sync(); // nodes written by earlier steps are visible
+                            const bool need = g.gl >= j && pre == -1 && !q_in_tree && wbest < bd && !(has2 && (pred_idx == widx || pred > j));
+                            TRRT_PROF({ pf[14]++; pf[15] += __popc(g.ballot(need)); })
+                            if (need) {
+                                expand_from<1>(solo, Q.m, a.P, Q.nx[widx], Q.ny[widx], Q.nth[widx], qx, qy, qth, Q.gx, Q.gy, Q.gth, e2);
+                                exist2 = -1;
+                                if (e2.code == EX_ACCEPT) exist2 = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e2.wx, e2.wy, e2.wth, probes, islot2);
+                                has2 = true; pred = -1; pred_idx = widx;
+                            }
+                        } else { TRRT_PROF(pf[13]++;) }
                         if (g.gl == j) {
                             near = widx;
-                            if (hit) { e = e2; exist = exist2; islot = islot2; }
-                            else {
-                                expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
-                                exist = -1;
-                                if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
-                            }
+                            e = e2; exist = exist2; islot = islot2;
                             word0 = pack_static();
                         }
                         wj = g.bcast(word0 | ((int)(exist >= 0) << 6), j);
@@ -742,6 +766,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         }
         c.probe += probes;
         g.sync(); // tree and index writes of this window are visible to every lane's next phase A
+        TRRT_PROF({ const unsigned long long s_ = clock64() - t4_; pf[7] += s_; pf[8] += s_ * s_ >> 10; const unsigned long long w_ = clock64() - t2_; pf[9] += w_ * w_ >> 10; })
         k0 += G;
         if (!running || k0 >= K - 1) { // query finished
             if (a.counters) { // fold the lane-private counters
@@ -753,6 +778,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
             have = false;
         }
     }
+    TRRT_PROF(if ((threadIdx.x & 31) == 0) for (int i_ = 0; i_ < 24; i_++) if (pf[i_]) atomicAdd(&g_phase_prof[i_], pf[i_]);)
 }
 
 } // namespace trrt
