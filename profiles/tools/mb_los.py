@@ -32,9 +32,9 @@ for lanes in (1, 16):
     os.environ["TRRT_LOS_LANES"] = str(lanes)
     run(f"rows  lanes {lanes:2d}", layout="rows")
 run("tiles default", layout="tiles")
-for coop in (4, 8, 16):
-    for rpw in (96, 128, 160, 192, 224, 256):
-        for refill in (6, 8, 12):
+for coop in (8, 16):
+    for rpw in (128, 256, 512):
+        for refill in (4, 8, 12):
             os.environ["TRRT_LOS_RPW"] = str(rpw); os.environ["TRRT_LOS_REFILL"] = str(refill); os.environ["TRRT_LOS_COOP"] = str(coop)
             run(f"tiles coop {coop:2d} rpw {rpw:4d} refill {refill:2d}", layout="tiles")
 os.environ.pop("TRRT_LOS_RPW"); os.environ.pop("TRRT_LOS_REFILL"); os.environ.pop("TRRT_LOS_COOP")

@@ -14,12 +14,13 @@
 //
 // A step of a lane (uniform control flow, no per-pixel branches):
 //   1. load the entry of the block from (block index, other-axis coordinate at the block's first pixel);
-//   2. run the literal running-error recurrence of the reference for the 8 pixels (D > 0 -> step, D -= 2*dmaj;
-//      D += 2*dmin) and record the window row of each pixel as a nibble of a PRMT selector;
+//   2. the reference's running-error recurrence (D > 0 -> step, D -= 2*dmaj; D += 2*dmin) in closed form: the window
+//      row of slot k is floor((u + k*2*dmin) / (2*dmaj)), u the phase of D at slot 0; the 8 quotients are exact
+//      FFMA + magic-number roundings and land as nibbles of a PRMT selector;
 //   3. shift the window to the entry's byte offset (funnel shift), gather the 8 rows with two PRMTs, and pick bit k of
 //      row k with the diagonal masks 0x08040201 / 0x80402010 restricted to the pixels that belong to the segment.
-// The first block starts at the aligned coordinate below the segment's first pixel: the recurrence is started at
-// D0 - klo*2*dmin, which is <= 0 until the first real pixel (no steps) and equals the reference's D0 there.
+// The first block starts at the aligned coordinate below the segment's first pixel, in the state the recurrence would
+// have had klo pixels before the segment, so that it reaches the reference's D0 and coordinate exactly at slot klo.
 //
 // Why refill.  Rays differ wildly in length and 88 % of the cfg-4 rays are blocked after a few pixels; with one
 // ray per thread a warp ran at 8 active lanes per instruction.  Here a warp owns a contiguous range of segments and
@@ -65,25 +66,46 @@ __global__ void tile_grid_kernel(const uint32_t *__restrict__ bits, int n_maps, 
     }
 }
 
+// Floor of a small quotient on the FMA pipe.  For integers 0 <= x < 2^20 and 0 < d < 2^16 with x / d < 16:
+//     floor(x / d) = low bits of  fmaf(x, rcp, hrm) + 1.5 * 2^23,   rcp = rn(1 / d),  hrm = rn(0.5 * rcp - 0.5).
+// (x + 0.5) / d is at least 0.5 / d >= 2^-17 away from every integer, the computed value is within 2^-19 of it
+// (rcp and hrm are correctly rounded, the product is exact in the fma, |value| < 16), so after the shift by -0.5 the
+// round-to-nearest of the magic addition is the floor.  tests/test_los_strip_model.py checks the formula against the
+// integer division on the boundary cases (x a multiple of d, one below) up to d = 65534.
+#define TRRT_LOS_MAGIC 12582912.0f   /* 1.5 * 2^23: float bits 0x4B400000 + n for the integer n it is added to */
+#define TRRT_LOS_MAGIC_BITS 0x4B400000u
+
 // One block of a ray: the 8 slots whose driving coordinate is A .. A+7 (A a multiple of 8), of which slots
-// klo .. min(7, aend - A) belong to the segment.  b, D are the other-axis coordinate and the running error at slot 0
-// and are advanced to slot 0 of the next block.  gtn = base of the orientation, moved on by one row of entries when the
-// ray travels towards larger coordinates (so that the entry index is (b >> 3) * tp + (A >> 3) either way).
+// klo .. min(7, aend - A) belong to the segment.  b is the other-axis coordinate at slot 0 and u the phase of the
+// reference's running error there, u = D - (2*dmin - 2*dmaj + 1) in [0, 2*dmaj): the recurrence of search.py:68-74 /
+// :87-93 (D > 0 -> step, D -= 2*dmaj; D += 2*dmin) keeps D in (2*dmin - 2*dmaj, 2*dmin], so after k pixels
+// u_k = (u + k*2*dmin) mod 2*dmaj and the number of steps taken is floor((u + k*2*dmin) / (2*dmaj)).
+// The 8 quotients come from the FMA pipe (see above) instead of 8 dependent compare / select / add triples on the
+// integer pipe, which is the one this kernel saturates.  u is kept as a float (an exact integer < 2^17).
+// gtn = base of the orientation, moved on by one row of entries when the ray travels towards larger coordinates (so
+// that the entry index is (b >> 3) * tp + (A >> 3) either way).  b and u are advanced to slot 0 of the next block.
 // Returns a non-zero word when one of the segment's pixels is blocked.
-__device__ __forceinline__ unsigned strip_block(const uint4 *__restrict__ gtn, int tp, int A, int aend, int klo, bool neg, int dmaj2, int dmin2,
-                                                int &b, int &D) {
+struct StripRay {
+    float rcp, slope, hrm, d8, dmaj2; // 1 / (2*dmaj), 2*dmin / (2*dmaj), 0.5 * rcp - 0.5, 8 * 2*dmin, 2*dmaj
+};
+__device__ __forceinline__ void strip_ray_consts(StripRay &r, float dmaj2f, float d8f) {
+    r.dmaj2 = dmaj2f; r.d8 = d8f;
+    r.rcp = __frcp_rn(dmaj2f);
+    r.slope = (d8f * 0.125f) * r.rcp;
+    r.hrm = 0.5f * r.rcp - 0.5f;
+}
+__device__ __forceinline__ unsigned strip_block(const uint4 *__restrict__ gtn, int tp, int A, int aend, int klo, bool neg, const StripRay &r, int &b,
+                                                float &u) {
     const uint4 wv = __ldg(gtn + ((b >> 3) * tp + (A >> 3)));
     const int sb = (b & 7) + (neg ? 1 : 0); // byte of the entry where the window starts
-    // literal recurrence of search.py:68-74 / :87-93; nibble k of sel = number of steps taken before slot k
-    unsigned sel = 0;
+    const float base = fmaf(u, r.rcp, r.hrm);
+    unsigned acc = 0; // nibble k = number of steps taken before slot k (slot 0: none)
 #pragma unroll
-    for (int k = 0; k < 7; k++) {
-        if (D > 0) { sel += 0x11111110u << (4 * k); D -= dmaj2; }
-        D += dmin2;
-    }
-    int j = (int)(sel >> 28);
-    if (D > 0) { j++; D -= dmaj2; }
-    D += dmin2;
+    for (int k = 1; k < 8; k++) acc += __float_as_uint(fmaf(r.slope, (float)k, base) + TRRT_LOS_MAGIC) << (4 * k);
+    unsigned sel = acc - 0xf4000000u; // the magic's exponent bits, summed over the seven shifts (mod 2^32)
+    const float r8 = fmaf(r.slope, 8.0f, base) + TRRT_LOS_MAGIC;
+    const int j = (int)(__float_as_uint(r8) - TRRT_LOS_MAGIC_BITS);
+    u = fmaf(-(r8 - TRRT_LOS_MAGIC), r.dmaj2, u + r.d8); // exact: integers below 2^24
     b += neg ? -j : j;
     const int q = sb >> 2, sh = (sb & 3) * 8;
     const unsigned r0 = q == 0 ? wv.x : q == 1 ? wv.y : wv.z;
@@ -116,7 +138,9 @@ __global__ void __launch_bounds__(TRRT_LOS_WARPS * 32, TRRT_LOS_CTAS_PER_SM)
 
     bool active = false, neg = false;
     const uint4 *gtn = tiles;
-    int idx = 0, a = 0, aend = 0, b = 0, D = 0, dmaj2 = 0, dmin2 = 0, klo = 0;
+    int idx = 0, a = 0, aend = 0, b = 0, klo = 0;
+    float u = 0.0f;
+    StripRay R = {0.5f, 0.0f, -0.25f, 0.0f, 2.0f};
 
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, active);
@@ -134,9 +158,17 @@ __global__ void __launch_bounds__(TRRT_LOS_WARPS * 32, TRRT_LOS_CTAS_PER_SM)
                         if (p0 > p1) { int t = p0; p0 = p1; p1 = t; t = q0; q0 = q1; q1 = t; } // search.py:48-56
                         const int dmaj = p1 - p0, dq = q1 - q0;
                         neg = dq < 0;
-                        dmaj2 = 2 * dmaj; dmin2 = 2 * abs(dq);
-                        klo = p0 & 7; a = p0 & ~7; aend = p1; b = q0;
-                        D = dmin2 - dmaj - klo * dmin2; // search.py:66 / :85, moved back to the block's first slot
+                        const int dmaj2 = dmaj ? 2 * dmaj : 2, dmin2 = 2 * abs(dq); // a single pixel never steps
+                        strip_ray_consts(R, (float)dmaj2, (float)(8 * dmin2));
+                        klo = p0 & 7; a = p0 & ~7; aend = p1;
+                        // The reference starts at D0 = 2*dmin - dmaj (search.py:66 / :85), i.e. phase dmaj - 1, at slot klo of
+                        // the first block.  Slot 0 gets the state the recurrence would have had klo pixels earlier: phase
+                        // (dmaj - 1 - klo*2*dmin) mod 2*dmaj and the other-axis coordinate that many steps back, so that
+                        // the block step needs no special case (the slots before klo are masked).
+                        const int w = (dmaj ? dmaj - 1 : 0) - klo * dmin2 + 7 * dmaj2; // >= 0
+                        const int qd = (int)(__float_as_uint(fmaf((float)w, R.rcp, R.hrm) + TRRT_LOS_MAGIC) - TRRT_LOS_MAGIC_BITS); // w / dmaj2
+                        u = (float)(w - qd * dmaj2);
+                        b = q0 + (neg ? 7 - qd : qd - 7);
                         gtn = tiles + ((size_t)(map_id ? __ldg(map_id + i) : 0) * 2 * epo + (low ? 0 : epo) + (neg ? 0 : tp));
                         idx = i;
                         active = true;
@@ -156,7 +188,7 @@ __global__ void __launch_bounds__(TRRT_LOS_WARPS * 32, TRRT_LOS_CTAS_PER_SM)
         if (nxt < cnt || na > coop_max) {
             // every lane advances its own ray by one block
             if (active) {
-                const unsigned bad = strip_block(gtn, tp, a, aend, klo, neg, dmaj2, dmin2, b, D);
+                const unsigned bad = strip_block(gtn, tp, a, aend, klo, neg, R, b, u);
                 a += 8;
                 klo = 0;
                 if (bad != 0u || a > aend) {
@@ -166,48 +198,49 @@ __global__ void __launch_bounds__(TRRT_LOS_WARPS * 32, TRRT_LOS_CTAS_PER_SM)
             }
         } else {
             // The warp's range is used up and few rays are left: the idle lanes join in.  The lanes are split into
-            // groups of G = 32 / nextpow2(na); group g takes the g-th remaining ray and member m its m-th next block.
-            // The state m blocks ahead follows from the invariant D in (2*dmin - 2*dmaj, 2*dmin]: D advances by
-            // 2*dmin per pixel modulo 2*dmaj, and the number of wraps is the number of steps.
+            // groups of G = 32 / nextpow2(na); group g takes the g-th remaining ray and member m its m-th next block,
+            // whose phase and coordinate follow from the same modular rule, m blocks at once (integer division).
             const int lg = 32 - __clz(na - 1), G = 32 >> lg, g = lane >> (5 - lg), m = lane & (G - 1);
             const unsigned srcu = __fns(act, 0, g + 1);
             const bool has = srcu < 32u;
             const int src = has ? (int)srcu : lane;
             const int sa = __shfl_sync(0xffffffffu, a, src), saend = __shfl_sync(0xffffffffu, aend, src);
-            int sbb = __shfl_sync(0xffffffffu, b, src), sD = __shfl_sync(0xffffffffu, D, src);
-            const int sdmaj2 = __shfl_sync(0xffffffffu, dmaj2, src), sdmin2 = __shfl_sync(0xffffffffu, dmin2, src);
+            int sbb = __shfl_sync(0xffffffffu, b, src);
+            float su = __shfl_sync(0xffffffffu, u, src);
+            const float sdmaj2f = __shfl_sync(0xffffffffu, R.dmaj2, src), sd8f = __shfl_sync(0xffffffffu, R.d8, src);
             const int sklo = __shfl_sync(0xffffffffu, klo, src);
             const bool sneg = __shfl_sync(0xffffffffu, (int)neg, src) != 0;
             const uint4 *sgtn = (const uint4 *)__shfl_sync(0xffffffffu, (unsigned long long)gtn, src);
             const int A = sa + 8 * m;
-            // the first block of a ray starts before the segment (D is not yet inside the invariant interval): alone
-            const bool work = has && A <= saend && (m == 0 || sklo == 0);
+            const bool work = has && A <= saend;
             unsigned bad = 0u;
             if (work) {
+                StripRay S;
+                strip_ray_consts(S, sdmaj2f, sd8f);
                 if (m > 0) {
-                    const int lo = sdmin2 - sdmaj2 + 1;
-                    const unsigned u = (unsigned)(sD + 8 * m * sdmin2 - lo), steps = u / (unsigned)sdmaj2; // sdmaj2 > 0: saend > sa
-                    sD = lo + (int)(u - steps * (unsigned)sdmaj2);
+                    const unsigned d2 = (unsigned)sdmaj2f, U = (unsigned)su + (unsigned)m * (unsigned)sd8f, steps = U / d2;
+                    su = (float)(U - steps * d2);
                     sbb += sneg ? -(int)steps : (int)steps;
                 }
-                bad = strip_block(sgtn, tp, A, saend, m == 0 ? sklo : 0, sneg, sdmaj2, sdmin2, sbb, sD);
+                bad = strip_block(sgtn, tp, A, saend, m == 0 ? sklo : 0, sneg, S, sbb, su);
             }
             const unsigned badm = __ballot_sync(0xffffffffu, bad != 0u);
-            // back to the owners: rank r among the active lanes = group r; the ray moves on nb blocks
-            const int r = __popc(act & lt), nb = klo ? 1 : G;
-            const int from = active ? r * G + nb - 1 : lane;
-            const int nb_ = __shfl_sync(0xffffffffu, sbb, from), nD_ = __shfl_sync(0xffffffffu, sD, from);
+            // back to the owners: rank r among the active lanes = group r; the ray moves on G blocks
+            const int r = __popc(act & lt);
+            const int from = active ? r * G + G - 1 : lane;
+            const int nb_ = __shfl_sync(0xffffffffu, sbb, from);
+            const float nu_ = __shfl_sync(0xffffffffu, su, from);
             if (active) {
                 const unsigned gm = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (r * G);
                 const bool blocked = (badm & gm) != 0u;
-                a += 8 * nb;
+                a += 8 * G;
                 klo = 0;
                 if (blocked || a > aend) {
                     out[idx] = blocked ? 0 : 1;
                     active = false;
                 } else {
                     b = nb_;
-                    D = nD_;
+                    u = nu_;
                 }
             }
         }
