@@ -92,6 +92,23 @@ def test_los_tiled_refill_mix(O, n):
     assert np.array_equal(got, p.los(seg, layout="rows").cpu().numpy().astype(bool))
 
 
+def test_los_long_rays_large_map(O):
+    """Side 16384: driving-axis lengths up to 16383 (divisors up to 32766 in the block walk's FMA floors), rays that
+    cross the whole map on a sparse map, both layouts and the oracle on a subset."""
+    n = 16384
+    free = util.synthetic_map(n, 0.0005, 16, 21)
+    rng = np.random.default_rng(5)
+    seg = rng.integers(0, n, size=(60000, 4)).astype(np.int32)
+    seg[:20000, 2:] = np.clip(seg[:20000, :2] + rng.integers(-3000, 3001, size=(20000, 2)), 0, n - 1)
+    seg[20000:20200] = [[0, 0, n - 1, n - 1], [n - 1, 0, 0, n - 1], [0, 5, n - 1, 6], [7, n - 1, 8, 0]] * 50
+    p = planner_for(free)
+    got = p.los(seg).cpu().numpy().astype(bool)
+    assert np.array_equal(got, p.los(seg, layout="rows").cpu().numpy().astype(bool))
+    sub = np.r_[0:2000, 20000:20200, 40000:42000]
+    assert np.array_equal(got[sub], O.lineofsight_batch(free, seg[sub], threads=4))
+    assert got.any() and not got.all()
+
+
 def test_los_empty_and_multimap(O):
     free = np.stack([util.synthetic_map(96, 0.2, 3, s) for s in (5, 6, 7)])
     from theta_rrt_b200 import OccupancyGrid, Planner
