@@ -516,6 +516,40 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args):
                                "unit": "expansions/s", "ms": msb, "queries": nqt,
                                "los_checks_per_sec": float(rb["n_los"].sum()) / (msb / 1e3),
                                "found": int((rb["status"] == 0).sum())}
+    # ---- cfg 5, the share of one GPU of an 8-GPU box: 4096 RRT queries (K = 1001) + 4096 Theta* queries, each bound
+    # to one of 64 random 256x256 maps (4x4-block Bernoulli obstacles, p = 0.15, default_rng(7 + map))
+    from theta_rrt_b200 import Params, samples
+    n_maps5, side5, nq5, K5 = 64, 256, 4096, 1001
+    maps5 = np.stack([synthetic_map(side5, 0.15, 4, 7 + m) for m in range(n_maps5)])
+    p5 = Planner(OccupancyGrid(maps5, device=dev), Params(tol_xy=0.0, K=K5))
+    r5 = np.random.default_rng(77)
+    mid_r = r5.integers(0, n_maps5, nq5).astype(np.int32)
+    mid_t = r5.integers(0, n_maps5, nq5).astype(np.int32)
+    free_cells = [np.argwhere(m) for m in maps5]
+    pick = lambda mids: np.stack([free_cells[m][r5.integers(len(free_cells[m]))] for m in mids])
+    a5, b5 = pick(mid_r), pick(mid_r)
+    starts5 = np.stack([a5[:, 1], a5[:, 0], r5.uniform(-180, 180, nq5)], 1).astype(np.float64)
+    goals5 = np.stack([b5[:, 1], b5[:, 0], r5.uniform(-180, 180, nq5)], 1).astype(np.float64)
+    sxy5 = np.empty((nq5, K5 - 1, 2), np.int32); sth5 = np.empty((nq5, K5 - 1))
+    for q in range(nq5):
+        sxy5[q], sth5[q] = samples.make_stream(((goals5[q, 0], goals5[q, 1]), goals5[q, 2]), K5 - 1, 500000 + q, (side5, side5))
+    ta, tb = pick(mid_t), pick(mid_t)
+    sg5 = torch.from_numpy(np.stack([ta[:, 1], ta[:, 0], tb[:, 1], tb[:, 0]], 1).astype(np.int32)).to(dev)
+    d5 = [torch.from_numpy(v).to(dev) for v in (starts5, goals5, sxy5, sth5)]
+    dm_r, dm_t = torch.from_numpy(mid_r).to(dev), torch.from_numpy(mid_t).to(dev)
+    res5 = {}
+
+    def step5():
+        res5["rrt"] = p5.rrt(*d5, K=K5, map_id=dm_r)
+        res5["theta"] = p5.theta(sg5, map_id=dm_t, path_cap=64)
+    ms5 = timed(step5, n=3, warm=1)
+    it5, ex5 = int(res5["rrt"].iters.sum()), int(res5["theta"].expanded.sum())
+    out["cfg5_mixed_share_of_one_gpu"] = {
+        "metric": "mixed_queries_per_sec", "value": 2 * nq5 / (ms5 / 1e3), "unit": "queries/s", "ms": ms5,
+        "rrt_queries": nq5, "K": K5, "theta_queries": nq5, "maps": f"{n_maps5} x {side5}x{side5}",
+        "rrt_expansions": it5, "theta_expansions": ex5, "expansions_per_sec": (it5 + ex5) / (ms5 / 1e3),
+        "theta_found": int((res5["theta"].status == 0).sum()),
+        "note": "1/8 of BASELINE cfg 5 (65536 queries over 8 GPUs), the RRT batch and the Theta* batch back to back"}
     if not args.skip_cpu:
         from oracle import c_oracle as O
         cores = os.cpu_count() or 1
