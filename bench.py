@@ -240,6 +240,8 @@ def main():
     ap.add_argument("--queries", type=int, default=NQ_PER_GPU, help="queries per GPU (default: the cfg-3 size)")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per query of the fused kernel (0 = auto)")
     ap.add_argument("--schedule", type=int, default=0, help="0 = speculative window (default), 1 = cooperative")
+    ap.add_argument("--valid-rows-d2h", action="store_true",
+                    help="e2e: pack the tree rows that exist on the device and fetch only those (Planner.rrt_host valid_rows_only)")
     ap.add_argument("--chunks", type=int, default=16, help="pieces of the e2e host-buffer pipeline (Planner.rrt_host)")
     ap.add_argument("--skip-secondary", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -263,6 +265,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist_on = world > 1
+    # one process per GPU: stay on the GPU's NUMA node before any pinned buffer exists (not at N = 1, where the CPU
+    # baseline legs of this process use every host core)
+    numa = shard.bind_host_to_device(local_rank) if (dist_on and not os.environ.get("TRRT_NO_NUMA_BIND")) else None
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -338,11 +343,18 @@ def main():
         "parent": ((nql, K), torch.int32), "u": ((nql, K, 5), torch.float64), "n_nodes": ((nql,), torch.int32),
         "sol": ((nql,), torch.int32), "status": ((nql,), torch.int32), "iters": ((nql,), torch.int32)}.items()}
     h2d = sum(t.numel() * t.element_size() for t in h_in)
-    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+    d2h_dense = sum(t.numel() * t.element_size() for t in h_out.values())
+    vro = args.valid_rows_d2h
+    # valid_rows_only: the rows that exist (68 B per node) are packed on the device and fetched with linear copies; the
+    # per-query scalars and the row index travel whole
+    if vro:
+        h_out["row_start"] = torch.empty(nql, dtype=torch.int64).pin_memory()
+    d2h = (n_nodes_total * 68 + sum(h_out[k].numel() * h_out[k].element_size() for k in ("n_nodes", "sol", "status", "iters", "row_start"))
+           if vro else d2h_dense)
 
     def step_e2e():
         # public host-buffer API: pinned inputs in, pinned trees out, transfers of one piece overlap the others' kernels
-        planner.rrt_host(*h_in, out=h_out, K=K, chunks=args.chunks, lanes=args.lanes, schedule=args.schedule)
+        planner.rrt_host(*h_in, out=h_out, K=K, chunks=args.chunks, lanes=args.lanes, schedule=args.schedule, valid_rows_only=vro)
 
     ms_e2e, _, _ = time_steps(torch, step_e2e, args.steps, 1, dist_on)  # every step waited for before the next starts
     serial_ms = float(sum(ms_e2e)) / args.steps
@@ -350,7 +362,8 @@ def main():
     # the same steps as a stream of batches: piece c of step i+1 queues behind piece c of step i, so the copies of one
     # step also overlap the planning of the next; the timed region still contains every step's H2D and D2H
     def step_e2e_streamed():
-        planner.rrt_host(*h_in, out=h_out, K=K, chunks=args.chunks, wait=False, lanes=args.lanes, schedule=args.schedule)
+        planner.rrt_host(*h_in, out=h_out, K=K, chunks=args.chunks, wait=False, lanes=args.lanes, schedule=args.schedule,
+                         valid_rows_only=vro)
 
     step_e2e_streamed(); planner.host_sync(); torch.cuda.synchronize()
     if dist_on:
@@ -370,8 +383,14 @@ def main():
     if dist_on:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = expansions_per_step_all * args.steps / (float(te.item()) / 1e3)
-    launches_e2e = args.steps * args.chunks
+    launches_e2e = args.steps * args.chunks * (2 if vro else 1)  # fused kernel (+ pack kernel) per piece
     assert int(h_out["n_nodes"].sum()) == n_nodes_total  # the host really received this step's trees
+    if vro:  # ... and the rows themselves: the last row of every tree against the resident result
+        last_dev = (keep["res"].n_nodes.long() - 1).clamp(min=0)
+        last_host = h_out["row_start"] + last_dev.cpu()
+        rows = torch.arange(nql, device=dev)
+        assert torch.equal(h_out["node_x"].view(-1)[last_host], keep["res"].node_x[rows, last_dev].cpu())
+        assert torch.equal(h_out["parent"].view(-1)[last_host], keep["res"].parent[rows, last_dev].cpu())
     keep.clear()
     del h_out
     torch.cuda.empty_cache()
@@ -388,9 +407,10 @@ def main():
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "expansions/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) / args.steps,
-                    "api": "Planner.rrt_host(pinned inputs, pinned outputs, chunks=%d, wait=False) per step, "
-                           "host_sync() after the last step" % args.chunks,
-                    "serial_ms_per_step": serial_ms,
+                    "api": "Planner.rrt_host(pinned inputs, pinned outputs, chunks=%d, wait=False%s) per step, "
+                           "host_sync() after the last step" % (args.chunks, ", valid_rows_only=True" if vro else ""),
+                    "d2h_dense_bytes_per_step": int(d2h_dense),
+                    "serial_ms_per_step": serial_ms, "host_numa_binding": numa,
                     "note": "steps are streamed: the transfers of a step overlap the planning of its neighbours; "
                             "serial_ms_per_step is the same call with every step completed before the next starts"},
             "gpu_launches": launches_timed, "gpu_launches_e2e": launches_e2e,

@@ -192,6 +192,19 @@ size_t trrt_rrt_workspace_bytes(int64_t n_queries, int32_t K);
 int trrt_rrt_batch(const trrt_rrt_args *args, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Result packing of K2.  The tree arrays of trrt_rrt_batch are [n_queries][K]
+ * blocks of which only the first n_nodes[q] rows exist (G, cameFrom as returned
+ * by rrt.rrt, rrt.py:204-206).  This copies those rows, device to device, to
+ * rows d_row_start[q] ... d_row_start[q] + n_nodes[q] - 1 of packed arrays
+ * (d_pu: 5 values per row), so that the host side can fetch a batch as one
+ * linear copy of the rows that exist.  d_row_start: int64 [n_queries], e.g. the
+ * exclusive prefix sum of d_n_nodes.  d_u / d_pu may both be NULL.
+ * ------------------------------------------------------------------------- */
+int trrt_rrt_pack_rows(int64_t n_queries, int32_t K, const int32_t *d_n_nodes, const int64_t *d_row_start, const double *d_node_x,
+                       const double *d_node_y, const double *d_node_th, const int32_t *d_parent, const double *d_u, double *d_px,
+                       double *d_py, double *d_pth, int32_t *d_pparent, double *d_pu, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Single-step entry points (batches of independent inputs, one result each);
  * they run the same device functions as the fused kernel.
  *   trrt_steer_batch  replaces rrt.steer (rrt.py:306-541).

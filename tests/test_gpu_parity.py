@@ -515,6 +515,57 @@ def test_rrt_host_pipeline_equals_resident(maps):
             assert np.array_equal(out["u"].numpy()[q, 1:n].view(np.int64), ref["u"][q, 1:n].view(np.int64))
 
 
+def test_rrt_host_valid_rows_only(maps):
+    """rrt_host(valid_rows_only=True): the rows that exist arrive packed, bit-identical to the resident result, at
+    row_start[q] of the flat host arrays; nothing else is touched."""
+    import torch
+    from theta_rrt_b200 import samples
+    free = maps["map1"]
+    nq, K = 41, 401
+    starts, goals = util.random_queries(free, nq, 987)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, 170 + q, free.shape)
+    p = planner_for(free, tol_xy=0.0)
+    ref = p.rrt(starts, goals, sxy, sth, K=K).host()
+    ins = [torch.from_numpy(a).pin_memory() for a in (starts, goals, sxy, sth)]
+    SENT = -12345.5
+    for chunks in (1, 6):
+        out = {"node_x": torch.full((nq, K), SENT, dtype=torch.float64).pin_memory(),
+               "node_y": torch.full((nq, K), SENT, dtype=torch.float64).pin_memory(),
+               "node_theta": torch.full((nq, K), SENT, dtype=torch.float64).pin_memory(),
+               "parent": torch.full((nq, K), -777, dtype=torch.int32).pin_memory(),
+               "u": torch.full((nq, K, 5), SENT, dtype=torch.float64).pin_memory(),
+               "n_nodes": torch.zeros(nq, dtype=torch.int32).pin_memory(), "status": torch.zeros(nq, dtype=torch.int32).pin_memory(),
+               "row_start": torch.full((nq,), -1, dtype=torch.int64).pin_memory()}
+        for _ in range(3):  # three streamed batches: both device result sets of every piece are used
+            p.rrt_host(*ins, out=out, K=K, chunks=chunks, wait=False, valid_rows_only=True)
+        p.host_sync()
+        torch.cuda.synchronize()
+        assert np.array_equal(out["n_nodes"].numpy(), ref["n_nodes"]) and np.array_equal(out["status"].numpy(), ref["status"])
+        rs = out["row_start"].numpy()
+        touched = np.zeros(nq * K, bool)
+        flat = {k: out[k].numpy().reshape(nq * K, -1) for k in ("node_x", "node_y", "node_theta", "parent", "u")}
+        for q in range(nq):
+            n = int(ref["n_nodes"][q])
+            c = next(c for c in range(chunks) if nq * c // chunks <= q < nq * (c + 1) // chunks)
+            lo = nq * c // chunks
+            assert rs[q] == lo * K + int(ref["n_nodes"][lo:q].sum()), q  # packed behind the earlier trees of its piece
+            rows = slice(int(rs[q]), int(rs[q]) + n)
+            touched[rows] = True
+            for k in ("node_x", "node_y", "node_theta"):
+                assert bits_equal(flat[k][rows, 0], ref[k][q, :n]), (k, q)
+            assert np.array_equal(flat["parent"][rows, 0], ref["parent"][q, :n])
+            assert np.array_equal(flat["u"][rows][1:].view(np.int64), ref["u"][q, 1:n].view(np.int64))
+        assert touched.sum() == int(ref["n_nodes"].sum()) < nq * K
+        for k in ("node_x", "node_y", "node_theta", "u"):
+            assert (flat[k][~touched] == SENT).all(), k
+        assert (flat["parent"][~touched] == -777).all()
+    with pytest.raises(ValueError):
+        bad = dict(out); bad["node_x"] = torch.zeros((nq, K), dtype=torch.float64)  # not pinned
+        p.rrt_host(*ins, out=bad, K=K, chunks=2, valid_rows_only=True)
+
+
 # ------------------------------------------------------------------ BASELINE full sizes: properties + exact subsets
 def test_cfg4_full_size_nearest_and_raycast(O):
     """BASELINE cfg 4 at full size: 8192 x 8192 grid, 2^20-node tree, 4096 nearest queries, 2^20 rays.

@@ -11,6 +11,7 @@
 //   rrt_kernel_coop<G>        same loop, G lanes cooperating on one iteration at a time
 //   wave_*                    same loop as scan / expand / re-expand / commit kernels (trrt_wave.cuh, experimental)
 //   steer / drive / arc batch kernels: single steps of K2 for the drop-in helpers and step-level parity tests
+//   rrt_pack_rows_kernel      the tree rows of K2 that exist, packed for the transfer to the host
 //   findnearest_kernel    rrt.findnearest over the edge log
 //   theta_kernel<G>       K3: A* / lazy Theta*, G lanes per query, G-ary heap
 //
@@ -1043,6 +1044,46 @@ int trrt_arc_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
     case 32: arc_batch_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(d_bits, H, W, wpr, d_map_id, n, d_in, d_blocked); break;
     default: return TRRT_ERR_INVALID_ARGUMENT;
     }
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+// ===========================================================================
+// packing of the tree rows that exist: query q's rows [0, n_nodes[q]) of the [n_queries][K] arrays of K2 go to rows
+// row_start[q] ... of packed arrays, so that a batch travels to the host as one linear copy of the valid rows (the
+// trees fill about half of their capacity on cfg 3).  One small CTA per query, grid-stride; device-to-device.
+// ===========================================================================
+__global__ void __launch_bounds__(128) rrt_pack_rows_kernel(int64_t nq, int K, const int32_t *__restrict__ n_nodes, const int64_t *__restrict__ row_start,
+                                                            const double *__restrict__ sx, const double *__restrict__ sy,
+                                                            const double *__restrict__ sth, const int32_t *__restrict__ sp,
+                                                            const double *__restrict__ su, double *__restrict__ ox, double *__restrict__ oy,
+                                                            double *__restrict__ oth, int32_t *__restrict__ op, double *__restrict__ ou) {
+    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        int n = __ldg(n_nodes + q);
+        n = n < 0 ? 0 : (n > K ? K : n);
+        const int64_t base = q * K, dst = __ldg(row_start + q);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            ox[dst + i] = sx[base + i];
+            oy[dst + i] = sy[base + i];
+            oth[dst + i] = sth[base + i];
+            op[dst + i] = sp[base + i];
+        }
+        if (su && ou)
+            for (int i = threadIdx.x; i < 5 * n; i += blockDim.x) ou[5 * dst + i] = su[5 * base + i];
+    }
+}
+
+int trrt_rrt_pack_rows(int64_t n_queries, int32_t K, const int32_t *d_n_nodes, const int64_t *d_row_start, const double *d_node_x,
+                       const double *d_node_y, const double *d_node_th, const int32_t *d_parent, const double *d_u, double *d_px, double *d_py,
+                       double *d_pth, int32_t *d_pparent, double *d_pu, void *stream) {
+    if (n_queries < 0 || K < 1) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n_queries == 0) return TRRT_OK;
+    if (!d_n_nodes || !d_row_start || !d_node_x || !d_node_y || !d_node_th || !d_parent || !d_px || !d_py || !d_pth || !d_pparent)
+        return TRRT_ERR_INVALID_ARGUMENT;
+    if ((d_u == nullptr) != (d_pu == nullptr)) return TRRT_ERR_INVALID_ARGUMENT;
+    const int64_t cap = (int64_t)sm_count() * 4, blocks = n_queries < cap ? n_queries : cap;
+    rrt_pack_rows_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(n_queries, K, d_n_nodes, d_row_start, d_node_x, d_node_y, d_node_th, d_parent,
+                                                                            d_u, d_px, d_py, d_pth, d_pparent, d_pu);
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }

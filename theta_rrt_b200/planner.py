@@ -223,7 +223,9 @@ class Planner:
             res._keep = (starts, goals, sample_xy, sample_th, mid)
         return res
 
-    def rrt_host(self, starts, goals, sample_xy, sample_th, out, K=None, chunks=4, wait=True, **kw):
+    _TREE = ("node_x", "node_y", "node_theta", "parent", "u")
+
+    def rrt_host(self, starts, goals, sample_xy, sample_th, out, K=None, chunks=4, wait=True, valid_rows_only=False, **kw):
         """rrt.rrt for a batch whose inputs and outputs live in (pinned) HOST memory: the queries are cut into
         `chunks` contiguous pieces, each on its own stream (host->device copy, fused kernel, device->host copy), so
         that the PCIe transfers of one piece overlap the planning of the others.  `out` maps RrtResult field names
@@ -232,50 +234,127 @@ class Planner:
         current stream waits for every piece (synchronise it before reading `out`).  With wait=False nothing waits:
         successive calls queue piece c of the next batch behind piece c of this one on the same stream, so the
         transfers of one batch also overlap the planning of the next (double-buffered streaming of batches); call
-        host_sync() before reading the outputs or reusing the host buffers."""
+        host_sync() before reading the outputs or reusing the host buffers.
+
+        valid_rows_only=True: a tree holds n_nodes[q] <= K nodes (about half of K on cfg 3) and only those rows are
+        brought back.  The rows of every piece are packed on the device (trrt_rrt_pack_rows) and fetched with one
+        linear copy per array; in the host arrays (contiguous pinned tensors of the usual [q, K(, 5)] shape, viewed as
+        flat row arrays) the rows of query q are rows out["row_start"][q] ... + n_nodes[q] - 1, anything else is not
+        touched.  `out` must contain n_nodes and row_start (int64 [q]).  The size of a piece's copy is known once its
+        node count has reached the host, so the copies of a batch are issued one call later (or in host_sync()), on
+        copy streams of their own, while the next batch is already being planned into a second set of buffers."""
         ins = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))
                for t in (starts, goals, sample_xy, sample_th)]
         nq = ins[0].shape[0]
         chunks = max(1, min(int(chunks), nq))
+        defer = bool(valid_rows_only)
+        if defer:
+            if "n_nodes" not in out or "row_start" not in out:
+                raise ValueError("valid_rows_only needs 'n_nodes' and 'row_start' among the outputs")
+            for k in self._TREE:
+                if k in out and not (out[k].is_pinned() and out[k].is_contiguous()):
+                    raise ValueError(f"valid_rows_only needs a contiguous pinned host tensor for '{k}'")
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
             if not hasattr(self, "_streams") or len(self._streams) < chunks:
                 self._streams = [torch.cuda.Stream(self.device) for _ in range(chunks)]
+                self._copy_streams = [torch.cuda.Stream(self.device) for _ in range(chunks)]
+            if not hasattr(self, "_host_cache"):
+                self._host_cache = {}
             start = torch.cuda.Event()
             start.record(main)
-            keep = []
+            keep, deferred = [], []
             for c in range(chunks):
                 lo, hi = nq * c // chunks, nq * (c + 1) // chunks
                 st = self._streams[c]
                 st.wait_event(start)
                 with torch.cuda.stream(st):
-                    # device buffers of a piece are allocated once and reused by later calls of the same shape
-                    key = (c, chunks, tuple((tuple(t[lo:hi].shape), t.dtype) for t in ins))
-                    cached = self._host_cache.get(key) if hasattr(self, "_host_cache") else None
+                    # device buffers of a piece are allocated once and reused by later calls of the same shape; with
+                    # deferred tree copies there are two result sets per piece, used alternately
+                    key = (c, chunks, defer, tuple((tuple(t[lo:hi].shape), t.dtype) for t in ins))
+                    cached = self._host_cache.get(key)
                     if cached is None:
-                        if not hasattr(self, "_host_cache"):
-                            self._host_cache = {}
-                        cached = ([torch.empty(t[lo:hi].shape, dtype=t.dtype, device=self.device) for t in ins], None)
-                    din, prev = cached
+                        cached = {"din": [torch.empty(t[lo:hi].shape, dtype=t.dtype, device=self.device) for t in ins],
+                                  "res": [None, None], "free": [None, None], "turn": 0,
+                                  "total": [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)],
+                                  "packed": [None, None]}
+                        self._host_cache[key] = cached
+                    turn = cached["turn"] if defer else 0
+                    cached["turn"] = 1 - turn if defer else 0
+                    if cached["free"][turn] is not None:
+                        st.wait_event(cached["free"][turn])  # the tree copies that still read this result set
+                        cached["free"][turn] = None
+                    din = cached["din"]
                     for d, t in zip(din, ins):
                         d.copy_(t[lo:hi], non_blocking=True)
-                    res = self.rrt(*din, K=K, work_key=("rrt", c), reuse=prev, **kw)
-                    self._host_cache[key] = (din, res)
+                    res = self.rrt(*din, K=K, work_key=("rrt", c), reuse=cached["res"][turn], **kw)
+                    cached["res"][turn] = res
                     for name, t in out.items():
+                        if defer and (name in self._TREE or name == "row_start"):
+                            continue
                         t[lo:hi].copy_(getattr(res, name), non_blocking=True)
+                    if defer:
+                        # pack the rows that exist; their number goes to a host word that belongs to this result set
+                        n64 = res.n_nodes.to(torch.int64)
+                        ends = torch.cumsum(n64, 0)
+                        starts_ = ends - n64
+                        pk = cached["packed"][turn]
+                        if pk is None:
+                            pk = {k: torch.empty_like(getattr(res, k)) for k in self._TREE if getattr(res, k) is not None}
+                            cached["packed"][turn] = pk
+                        _lib.check(self.lib.trrt_rrt_pack_rows(
+                            hi - lo, res.K, res.n_nodes.data_ptr(), starts_.data_ptr(), res.node_x.data_ptr(), res.node_y.data_ptr(),
+                            res.node_theta.data_ptr(), res.parent.data_ptr(), res.u.data_ptr() if res.u is not None else None,
+                            pk["node_x"].data_ptr(), pk["node_y"].data_ptr(), pk["node_theta"].data_ptr(), pk["parent"].data_ptr(),
+                            pk["u"].data_ptr() if res.u is not None else None, st.cuda_stream), "trrt_rrt_pack_rows")
+                        cached["total"][turn].copy_(ends[-1:], non_blocking=True)
+                        out["row_start"][lo:hi].copy_(starts_ + lo * res.K, non_blocking=True)
+                        keep.append((n64, ends, starts_))
                     keep.append((din, res))
                 done = torch.cuda.Event()
                 done.record(st)
-                if wait:
+                if defer:
+                    deferred.append((c, lo, hi, res, done, out, cached, turn))
+                elif wait:
                     main.wait_event(done)
                 else:
                     self._pending = [e for e in getattr(self, "_pending", []) if not e.query()] + [done]
             self._inflight = keep  # tensors stay referenced until the next call
+            if defer:
+                # the previous batch first (its n_nodes are on the host by now), this one only if the caller waits
+                previous, self._deferred = getattr(self, "_deferred", []), deferred
+                self._issue_tree_copies(previous)
+                if wait:
+                    self._issue_tree_copies(self._deferred)
+                    self._deferred = []
+                    self.host_sync()
         return out
+
+    def _issue_tree_copies(self, items):
+        """Second half of rrt_host(valid_rows_only=True) for the pieces in `items`: wait until the piece's row count is on
+        the host, then fetch its packed rows with one linear copy per array on the piece's copy stream."""
+        for c, lo, hi, res, done, out, cached, turn in items:
+            done.synchronize()
+            total = min(max(int(cached["total"][turn]), 0), (hi - lo) * res.K)
+            cs = self._copy_streams[c]
+            cs.wait_event(done)
+            with torch.cuda.stream(cs):
+                for name, src in cached["packed"][turn].items():
+                    if name not in out:
+                        continue
+                    m = 5 if name == "u" else 1
+                    out[name].view(-1)[lo * res.K * m:lo * res.K * m + total * m].copy_(src.view(-1)[:total * m], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(cs)
+            cached["free"][turn] = copied
+            self._pending = [e for e in getattr(self, "_pending", []) if not e.query()] + [copied]
 
     def host_sync(self):
         """Make the planner's current stream wait for every piece enqueued by rrt_host(..., wait=False)."""
         with torch.cuda.device(self.device):
+            if getattr(self, "_deferred", None):
+                self._issue_tree_copies(self._deferred)
+                self._deferred = []
             main = torch.cuda.current_stream(self.device)
             for e in getattr(self, "_pending", []):
                 main.wait_event(e)

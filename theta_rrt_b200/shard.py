@@ -7,8 +7,41 @@ records at the end (NCCL over NVLink on GPUs, gloo in the CPU tests).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def device_numa_node(device_index: int):
+    """NUMA node of a CUDA device from sysfs (None when the platform does not say)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_host_to_device(device_index: int):
+    """One process per GPU: keep this process (and therefore the pinned staging buffers it allocates next, first touch)
+    on the NUMA node its GPU hangs off, so that the host side of the H2D / D2H streams of different ranks does not
+    cross the socket interconnect.  Returns a description of what was done (for the bench line)."""
+    node = device_numa_node(device_index)
+    if node is None:
+        return {"numa_node": None}
+    try:
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # not fatal: the run is merely not bound
+        return {"numa_node": node, "error": str(e)}
 
 
 def shard_range(n_queries: int, rank: int, world: int):
