@@ -258,7 +258,8 @@ class Planner:
             main = torch.cuda.current_stream(self.device)
             if not hasattr(self, "_streams") or len(self._streams) < chunks:
                 self._streams = [torch.cuda.Stream(self.device) for _ in range(chunks)]
-                self._copy_streams = [torch.cuda.Stream(self.device) for _ in range(chunks)]
+                # packing and fetching a finished piece must not queue behind the persistent kernels of the other pieces
+                self._copy_streams = [torch.cuda.Stream(self.device, priority=-1) for _ in range(chunks)]
             if not hasattr(self, "_host_cache"):
                 self._host_cache = {}
             start = torch.cuda.Event()
@@ -294,25 +295,32 @@ class Planner:
                             continue
                         t[lo:hi].copy_(getattr(res, name), non_blocking=True)
                     if defer:
-                        # pack the rows that exist; their number goes to a host word that belongs to this result set
-                        n64 = res.n_nodes.to(torch.int64)
-                        ends = torch.cumsum(n64, 0)
-                        starts_ = ends - n64
-                        pk = cached["packed"][turn]
-                        if pk is None:
-                            pk = {k: torch.empty_like(getattr(res, k)) for k in self._TREE if getattr(res, k) is not None}
-                            cached["packed"][turn] = pk
-                        _lib.check(self.lib.trrt_rrt_pack_rows(
-                            hi - lo, res.K, res.n_nodes.data_ptr(), starts_.data_ptr(), res.node_x.data_ptr(), res.node_y.data_ptr(),
-                            res.node_theta.data_ptr(), res.parent.data_ptr(), res.u.data_ptr() if res.u is not None else None,
-                            pk["node_x"].data_ptr(), pk["node_y"].data_ptr(), pk["node_theta"].data_ptr(), pk["parent"].data_ptr(),
-                            pk["u"].data_ptr() if res.u is not None else None, st.cuda_stream), "trrt_rrt_pack_rows")
-                        cached["total"][turn].copy_(ends[-1:], non_blocking=True)
-                        out["row_start"][lo:hi].copy_(starts_ + lo * res.K, non_blocking=True)
-                        keep.append((n64, ends, starts_))
+                        # pack the rows that exist, on the piece's (high-priority) copy stream; their number goes to a
+                        # host word that belongs to this result set
+                        planned = torch.cuda.Event()
+                        planned.record(st)
+                        cs = self._copy_streams[c]
+                        cs.wait_event(planned)
+                        with torch.cuda.stream(cs):
+                            n64 = res.n_nodes.to(torch.int64)
+                            ends = torch.cumsum(n64, 0)
+                            starts_ = ends - n64
+                            pk = cached["packed"][turn]
+                            if pk is None:
+                                pk = {k: torch.empty_like(getattr(res, k)) for k in self._TREE if getattr(res, k) is not None}
+                                cached["packed"][turn] = pk
+                            _lib.check(self.lib.trrt_rrt_pack_rows(
+                                hi - lo, res.K, res.n_nodes.data_ptr(), starts_.data_ptr(), res.node_x.data_ptr(),
+                                res.node_y.data_ptr(), res.node_theta.data_ptr(), res.parent.data_ptr(),
+                                res.u.data_ptr() if res.u is not None else None, pk["node_x"].data_ptr(), pk["node_y"].data_ptr(),
+                                pk["node_theta"].data_ptr(), pk["parent"].data_ptr(),
+                                pk["u"].data_ptr() if res.u is not None else None, cs.cuda_stream), "trrt_rrt_pack_rows")
+                            cached["total"][turn].copy_(ends[-1:], non_blocking=True)
+                            out["row_start"][lo:hi].copy_(starts_ + lo * res.K, non_blocking=True)
+                            keep.append((n64, ends, starts_))
                     keep.append((din, res))
                 done = torch.cuda.Event()
-                done.record(st)
+                done.record(self._copy_streams[c] if defer else st)
                 if defer:
                     deferred.append((c, lo, hi, res, done, out, cached, turn))
                 elif wait:
