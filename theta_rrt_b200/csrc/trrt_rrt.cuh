@@ -13,10 +13,12 @@
 //    scan (the warp stages the tree through shared memory once per window), steer, clearance rays,
 //    re-drive and edge raster.  The window is then committed in iteration order; every inserted
 //    node is broadcast so that later lanes can correct their snapshot winner (new nodes have
-//    higher indices, so the snapshot winner keeps ties) and their two `in G` flags.  Only when a
-//    node of the window is strictly nearer (2.9% of the cfg-3 iterations) is the iteration
-//    expanded again, from that node, by its own lane.  The committed sequence is exactly the
-//    sequential loop.  One persistent kernel, groups pull queries from a counter.
+//    higher indices, so the snapshot winner keeps ties) and their `in G` flags.  When a node of the
+//    window is strictly nearer (2.9% of the cfg-3 iterations) the iteration has to be expanded
+//    again from that node: the lanes this will happen to are predicted before the commit and
+//    expand together (phase A, part 3); what the prediction misses is expanded in lane-parallel
+//    rounds inside the commit.  The committed sequence is exactly the sequential loop.  One
+//    persistent kernel, groups pull queries from a counter.
 //
 //  * phase-split (schedule 2, experimental, trrt_wave.cuh): the same window as separate scan /
 //    expand / re-expand / commit kernels over all queries.
@@ -398,12 +400,15 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
 // Phase A (lane j = iteration k0+j, all lanes in parallel, everything in registers):
 //   sample -> freespace(qrand) -> `qrand in G` probe of the snapshot index -> private nearest scan over the
 //   snapshot -> steer / clearance rays / re-drive / edge raster (expand_from<1>) -> `qnew in G` probe.
+// Phase A, part 3: the lanes whose nearest node will be a node of their own window are predicted from the tentative
+//   outcomes and expand again, together, from the predicted node (second outcome record e2).
 // Phase B (commit, iteration order, uniform control flow): step j only moves a few words out of lane j with
 //   shuffles.  When a step inserts a node, lane j writes it (tree arrays + index) and broadcasts its coordinates;
-//   every lane folds that node into (a) its distance-to-nodes-of-this-window minimum and (b) its two equality
+//   every lane folds that node into (a) its distance-to-nodes-of-this-window minimum and (b) its equality
 //   flags, so later steps need neither a reduction nor an index probe.  If a node of the window is strictly nearer
-//   than lane j's snapshot winner (new nodes have higher indices, so ties stay with the snapshot), lane j alone
-//   re-expands its iteration from that node before committing.
+//   than lane j's snapshot winner (new nodes have higher indices, so ties stay with the snapshot), lane j commits
+//   e2 when it was expanded from exactly that node; otherwise all lanes from j on that lack an expansion from their
+//   nearest node so far expand in one round.
 // ---------------------------------------------------------------------------
 #ifndef TRRT_SCAN_AHEAD
 #define TRRT_SCAN_AHEAD 1024
