@@ -45,3 +45,18 @@ def test_gather_records_world2(n):
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+def test_bind_host_to_device_is_harmless_without_topology():
+    """shard.bind_host_to_device: on a box without a GPU (or without NUMA information in sysfs) it reports that and
+    leaves the CPU affinity of the process alone."""
+    import os
+    from theta_rrt_b200 import shard
+    before = os.sched_getaffinity(0)
+    info = shard.bind_host_to_device(0)
+    assert isinstance(info, dict) and "numa_node" in info
+    if info["numa_node"] is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        assert os.sched_getaffinity(0) <= before
+        os.sched_setaffinity(0, before)
