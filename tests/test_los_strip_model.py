@@ -141,3 +141,26 @@ def test_strip_model_clear_map_all_directions():
         for y1 in range(0, n, 3):
             assert los_model(strips, tp, n, (23, 17, x1, y1), coop_every=2)
             assert los_model(strips, tp, n, (x1, y1, 0, n - 1), coop_every=3)
+
+
+def test_strip_model_property_random_maps():
+    """Property test (hypothesis): any square map from 1 x 1 up, any density, any segments (also out of bounds, zero
+    length, reversed): the strip model and the oracle's literal search.lineofsight agree, and the result does not depend
+    on the direction the segment is given in (search.py:47-56 canonicalises)."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import c_oracle as O
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 40), st.floats(0.0, 0.6), st.integers(0, 2 ** 31 - 1))
+    def check(n, p, seed):
+        rng = np.random.default_rng(seed)
+        free = rng.random((n, n)) >= p
+        strips, tp = build_strips(free)
+        seg = rng.integers(-1, n + 1, size=(60, 4)).astype(np.int32)
+        ref = O.lineofsight_batch(free, seg)
+        got = np.array([los_model(strips, tp, n, s, coop_every=int(rng.integers(0, 4))) for s in seg])
+        assert np.array_equal(got, ref)
+        rev = np.array([los_model(strips, tp, n, s[[2, 3, 0, 1]]) for s in seg])
+        assert np.array_equal(rev, ref)
+
+    check()
