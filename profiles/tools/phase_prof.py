@@ -35,7 +35,7 @@ lib.trrt_debug_phase_prof(buf)
 v = [int(x) for x in buf]
 W = v[10]
 print(f"kernel {a.elapsed_time(b):.2f} ms, windows (warp x window) {W}, iterations {int(r.iters.sum())}")
-names = [("scan (to barrier arrival)", 0, 1), ("barrier wait", 2, None), ("expansion", 3, 4), ("predicted re-expansion", 5, 6), ("commit", 7, 8)]
+names = [("scan (to barrier arrival)", 0, 1), ("barrier wait", 2, None), ("expansion", 3, 4), ("pass + commit", 7, 8)]
 tot = v[0] + v[2] + v[3] + v[5] + v[7]
 for nm, i, j in names:
     mean = v[i] / W
@@ -44,6 +44,6 @@ for nm, i, j in names:
         var = v[j] * 1024 / W - mean * mean
         line += f"  std {max(var, 0) ** 0.5:9.0f}"
     print(line)
-post = (v[3] + v[5] + v[7]) / W
+post = (v[3] + v[7]) / W
 print(f"  after-barrier work per window: mean {post:.0f}, std {max(v[9] * 1024 / W - post * post, 0) ** 0.5:.0f}")
-print(f"  windows with a predicted lane {v[11]} ({100 * v[11] / W:.1f}%), predicted lanes {v[12]}, hits {v[13]}, re-expansion rounds inside the commit {v[14]} with {v[15]} lanes")
+print(f"  iterations committed per window: {v[17] / max(v[16], 1):.2f} of 32")

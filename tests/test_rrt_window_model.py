@@ -1,6 +1,7 @@
 """CPU model of the control logic of the fused RRT kernel's speculative window (csrc/trrt_rrt.cuh, schedule 0):
-snapshot nearest -> tentative expansion -> predicted re-expansions (phase A, part 3) -> commit in iteration order with
-the folded window minimum / equality flags and the lane-parallel re-expansion rounds.
+snapshot nearest -> tentative expansion -> forward fold of the inserted nodes (window minimum / equality flags) ->
+parallel commit of the lanes before the first one whose nearest node is a node of its own window; the next window
+starts at that lane.
 
 The exactness of that schedule does not depend on WHAT an expansion computes, only on it being a deterministic function
 of (nearest node, sample, map).  So the model runs a toy expansion on an integer lattice (many exact distance ties,
@@ -63,93 +64,80 @@ def sequential(start, samples):
 
 
 def windowed(start, samples, G, stats):
-    """The kernel's schedule, lane by lane, with the same state per lane and the same folds."""
+    """The kernel's schedule, lane by lane, with the same state per lane and the same folds: a window of up to G
+    iterations against a snapshot; the inserting lanes are folded forward in iteration order; the window commits up to the
+    first lane whose nearest node was inserted in this very window, and the next window starts at that iteration."""
     nodes, parent, index, codes, nears = [start], [-1], {start: 0}, [], []
-    for k0 in range(0, len(samples), G):
+    k0 = 0
+    while k0 < len(samples):
         win = samples[k0:k0 + G]
         L = len(win)
         n0 = len(nodes)
         snap = dict(index)  # the index as the window starts
-        # ---- phase A, parts 1 and 2 (against the snapshot)
+        # ---- phase A (against the snapshot)
         pre = [blocked(s) for s in win]
         q_in_tree = [(not pre[j]) and win[j] in snap for j in range(L)]
-        live = [not pre[j] and not q_in_tree[j] for j in range(L)]
         bd, near, e, exist = [None] * L, [-1] * L, [None] * L, [-1] * L
         for j in range(L):
-            if live[j]:
+            if not pre[j] and not q_in_tree[j]:
                 near[j] = min(range(n0), key=lambda i: (d2(win[j], nodes[i]), i))
                 bd[j] = d2(win[j], nodes[near[j]])
                 e[j] = expand(nodes[near[j]], win[j])
                 if e[j][0] == "accept":
                     exist[j] = snap.get(e[j][1], -1)
-        # ---- phase A, part 3: predicted re-expansions
-        pred, has2, e2, exist2, pred_idx = [-1] * L, [False] * L, [None] * L, [-1] * L, [-2] * L
-        for j in range(L):
-            if not live[j]:
-                continue
-            pbest = bd[j]
-            for i in range(j):
-                if live[i] and e[i][0] == "accept" and exist[i] < 0:  # will_insert
-                    d = d2(win[j], e[i][1])
-                    if d < pbest:
-                        pbest, pred[j] = d, i
-            if pred[j] >= 0:
-                has2[j] = True
-                e2[j] = expand(e[pred[j]][1], win[j])
-                if e2[j][0] == "accept":
-                    exist2[j] = snap.get(e2[j][1], -1)
-        # ---- phase B: commit in iteration order
-        wbest, widx = [None] * L, [-1] * L
-        for j in range(L):
+        # ---- pass: fold the inserting lanes forward until a lane has moved
+        moved = [False] * L
+        done, last = [], -1
+        while True:
+            live = [not pre[l] and not q_in_tree[l] for l in range(L)]
+            stop = [l for l in range(L) if live[l] and moved[l]]
+            ins = [l for l in range(L) if l > last and live[l] and not moved[l] and e[l][0] == "accept" and exist[l] < 0]
+            fs = stop[0] if stop else L
+            ni = ins[0] if ins else L
+            if ni >= fs:
+                break
+            idx_i = n0 + len(done)
+            done.append(ni)
+            last = ni
+            w = e[ni][1]
+            for l in range(ni + 1, L):  # every later lane folds the node
+                if bd[l] is not None and d2(win[l], w) < bd[l]:
+                    moved[l] = True  # strictly nearer than the snapshot winner: ties stay with the lower index
+                if win[l] == w:
+                    q_in_tree[l] = True
+                if exist[l] < 0 and e[l] is not None and e[l][0] == "accept" and e[l][1] == w:
+                    exist[l] = idx_i
+        done = [l for l in done if l < fs]
+        stats["windows"] += 1
+        stats["lanes"] += fs
+        assert fs >= 1  # lane 0 has no predecessor in its window
+        # ---- commit of lanes [0, fs), all at once
+        target = {}
+        for l in range(fs):
             code, near_j = None, -1
-            if pre[j]:
+            if pre[l]:
                 code = BLOCKED
-            elif q_in_tree[j]:
+            elif q_in_tree[l]:
                 code = IN_TREE
             else:
-                moved = wbest[j] is not None and wbest[j] < bd[j]
-                if moved:
-                    hit = has2[j] and widx[j] == pred_idx[j]
-                    if not hit:
-                        stats["rounds"] += 1
-                        for l in range(j, L):  # every lane from j on that lacks an expansion from its nearest node so far
-                            need = (not pre[l]) and (not q_in_tree[l]) and wbest[l] is not None and wbest[l] < bd[l] \
-                                and not (has2[l] and (pred_idx[l] == widx[l] or pred[l] > j))
-                            if need:
-                                e2[l] = expand(nodes[widx[l]], win[l])
-                                exist2[l] = index.get(e2[l][1], -1) if e2[l][0] == "accept" else -1
-                                has2[l], pred[l], pred_idx[l] = True, -1, widx[l]
-                    else:
-                        stats["hits"] += 1
-                    near[j], e[j], exist[j] = widx[j], e2[j], exist2[j]
-                near_j = near[j]
-                kind, w = e[j]
+                near_j = near[l]
+                kind, w = e[l]
                 if kind != "accept":
                     code = kind
                 else:
-                    idx = exist[j]
-                    if idx < 0:
-                        idx = len(nodes)
-                        nodes.append(w); parent.append(-1); index[w] = idx
-                        code = NEW
-                        for l in range(j + 1, L):  # every later lane folds the new node
-                            d = d2(win[l], w)
-                            if wbest[l] is None or d < wbest[l]:
-                                wbest[l], widx[l] = d, idx
-                            if win[l] == w:
-                                q_in_tree[l] = True
-                            if exist[l] < 0 and e[l] is not None and e[l][0] == "accept" and e[l][1] == w:
-                                exist[l] = idx
-                            if has2[l]:
-                                if pred[l] == j:
-                                    pred_idx[l] = -2 if moved else idx
-                                if exist2[l] < 0 and e2[l][0] == "accept" and e2[l][1] == w:
-                                    exist2[l] = idx
+                    if exist[l] >= 0:
+                        idx, code = exist[l], EXISTING
                     else:
-                        code = EXISTING
+                        idx, code = n0 + done.index(l), NEW
                     if idx != near_j:
-                        parent[idx] = near_j
+                        target[idx] = near_j  # the last lane that targets a node wins (rrt.py:188)
             codes.append(code); nears.append(near_j)
+        for l in done:
+            w = e[l][1]
+            nodes.append(w); parent.append(-1); index[w] = len(nodes) - 1
+        for idx, nr in target.items():
+            parent[idx] = nr
+        k0 += fs
     return nodes, parent, codes, nears
 
 
@@ -169,7 +157,7 @@ def test_window_schedule_equals_sequential_loop(G, seed, side, clustered):
     samples = make_samples(rng, side, 700, clustered)
     start = (side // 8, side // 8, 0)
     ref = sequential(start, samples)
-    stats = {"hits": 0, "rounds": 0}
+    stats = {"windows": 0, "lanes": 0}
     got = windowed(start, samples, G, stats)
     assert got[0] == ref[0], "nodes"
     assert got[1] == ref[1], "parents"
@@ -177,7 +165,7 @@ def test_window_schedule_equals_sequential_loop(G, seed, side, clustered):
     assert got[3] == ref[3], "nearest indices"
     assert {NEW, EXISTING, BLOCKED, STEER, ARC} <= set(ref[2]), set(ref[2])  # the toy exercises the outcomes
     if clustered and G == 32:
-        assert stats["hits"] > 0 and stats["rounds"] > 0, stats  # both the prediction and the fallback rounds ran
+        assert stats["lanes"] < G * (stats["windows"] - 1), stats  # some windows were cut short by a moved lane
 
 
 def test_window_model_sees_samples_on_nodes():
@@ -187,5 +175,5 @@ def test_window_model_sees_samples_on_nodes():
     ref = sequential((5, 5, 0), samples)
     assert IN_TREE in ref[2]
     for G in (4, 32):
-        got = windowed((5, 5, 0), samples, G, {"hits": 0, "rounds": 0})
+        got = windowed((5, 5, 0), samples, G, {"windows": 0, "lanes": 0})
         assert got == ref

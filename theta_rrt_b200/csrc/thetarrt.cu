@@ -9,7 +9,6 @@
 //   nearest_final_kernel      cross-slice reduction with lowest-index ties
 //   rrt_kernel_spec<G>    K2: fused rrt.rrt loop, speculative window of G iterations, persistent (trrt_rrt.cuh)
 //   rrt_kernel_coop<G>        same loop, G lanes cooperating on one iteration at a time
-//   wave_*                    same loop as scan / expand / re-expand / commit kernels (trrt_wave.cuh, experimental)
 //   steer / drive / arc batch kernels: single steps of K2 for the drop-in helpers and step-level parity tests
 //   rrt_pack_rows_kernel      the tree rows of K2 that exist, packed for the transfer to the host
 //   findnearest_kernel    rrt.findnearest over the edge log
@@ -29,7 +28,6 @@
 #include "trrt_device.cuh"
 #include "trrt_los.cuh"
 #include "trrt_rrt.cuh"
-#include "trrt_wave.cuh"
 
 using namespace trrt;
 
@@ -914,8 +912,8 @@ static int rrt_tsize(int K) {
 }
 size_t trrt_rrt_workspace_bytes(int64_t n_queries, int32_t K) {
     if (n_queries <= 0 || K <= 0) return 256;
-    // [work counter | hash tables | window records of the phase-split schedule]
-    return 256 + (size_t)n_queries * (size_t)rrt_tsize(K) * sizeof(int32_t) + wave_bytes(n_queries);
+    // [work counter | hash tables]
+    return 256 + (size_t)n_queries * (size_t)rrt_tsize(K) * sizeof(int32_t);
 }
 
 static BikeParams to_dev(const trrt_params &p) {
@@ -988,19 +986,6 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         RrtDev *dp = &d;
         void *kargs[] = {(void *)dp};
         CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)blocks), dim3(threads), kargs, smem, st));
-    } else if (A.schedule == 2) { // phase-split: three kernels per window over all queries (trrt_wave.cuh)
-        if (G != 32) return TRRT_ERR_INVALID_ARGUMENT;
-        const WaveDev w = wave_carve((char *)A.d_work + 256 + (size_t)A.n_queries * d.tsize * sizeof(int32_t), A.n_queries);
-        const unsigned gw = (unsigned)((A.n_queries * 32 + TRRT_WAVE_THREADS - 1) / TRRT_WAVE_THREADS);
-        const unsigned gs = (unsigned)((A.n_queries * 32 + TRRT_WAVE_SMALL - 1) / TRRT_WAVE_SMALL);
-        CUDA_TRY(cudaMemsetAsync(d.next_query, 0, 2 * sizeof(unsigned long long), st));
-        wave_init<<<gw, TRRT_WAVE_THREADS, 0, st>>>(d, w);
-        for (int k0 = 0; k0 < A.K - 1; k0 += 32) {
-            wave_scan<<<gw, TRRT_WAVE_THREADS, 0, st>>>(d, w, k0);
-            wave_expand<<<gs, TRRT_WAVE_SMALL, 0, st>>>(d, w);
-            wave_reexpand<<<gs, TRRT_WAVE_SMALL, 0, st>>>(d, w);
-            wave_commit<<<gs, TRRT_WAVE_SMALL, 0, st>>>(d, w, k0);
-        }
     } else return TRRT_ERR_INVALID_ARGUMENT;
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;

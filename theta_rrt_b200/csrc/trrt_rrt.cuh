@@ -106,6 +106,12 @@ __device__ __forceinline__ void tree_insert_from(int32_t *tab, int tmask, int sl
     tab[s] = idx + 1;
 }
 
+// the same for lanes of one warp inserting different keys at the same time (parallel segment commit)
+__device__ __forceinline__ void tree_insert_cas(int32_t *tab, int tmask, int slot, int idx) {
+    unsigned s = (unsigned)slot;
+    while (atomicCAS(tab + s, 0, idx + 1) != 0) s = (s + 1) & (unsigned)tmask;
+}
+
 // Outcome of one iteration from "nearest node chosen" to "edge tested" (rrt.py:161-176).
 enum { EX_ACCEPT = 100 }; // edge is free: proceed to insert (rrt.py:179)
 struct Expand {
@@ -395,20 +401,21 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
 }
 
 // ---------------------------------------------------------------------------
-// schedule 0: speculative window of G iterations (see the header comment)
+// schedule 0: speculative window of up to G iterations (see the header comment)
 //
 // Phase A (lane j = iteration k0+j, all lanes in parallel, everything in registers):
-//   sample -> freespace(qrand) -> `qrand in G` probe of the snapshot index -> private nearest scan over the
-//   snapshot -> steer / clearance rays / re-drive / edge raster (expand_from<1>) -> `qnew in G` probe.
-// Phase A, part 3: the lanes whose nearest node will be a node of their own window are predicted from the tentative
-//   outcomes and expand again, together, from the predicted node (second outcome record e2).
-// Phase B (commit, iteration order, uniform control flow): step j only moves a few words out of lane j with
-//   shuffles.  When a step inserts a node, lane j writes it (tree arrays + index) and broadcasts its coordinates;
-//   every lane folds that node into (a) its distance-to-nodes-of-this-window minimum and (b) its equality
-//   flags, so later steps need neither a reduction nor an index probe.  If a node of the window is strictly nearer
-//   than lane j's snapshot winner (new nodes have higher indices, so ties stay with the snapshot), lane j commits
-//   e2 when it was expanded from exactly that node; otherwise all lanes from j on that lack an expansion from their
-//   nearest node so far expand in one round.
+//   sample -> freespace(qrand) -> `qrand in G` probe of the snapshot index -> nearest scan over the snapshot ->
+//   steer / clearance rays / re-drive / edge raster (expand_from<1>) -> `qnew in G` probe.
+// Pass (registers and shuffles only): the lanes that insert a node are walked in iteration order; each one's node is
+//   folded into the later lanes (distance-to-nodes-of-this-window minimum, `qrand in G`, `qnew in G`).  New nodes have
+//   higher indices than the snapshot, so the snapshot winner keeps ties (first-minimum semantics of np.argmin).  The
+//   walk stops at the first lane f whose nearest node is no longer its snapshot winner: what lanes 0..f-1 computed
+//   is exactly what the sequential loop computes for them.
+// Commit: lanes [0, f) write their results TOGETHER -- node indices by prefix popcount, tree rows, index slots
+//   (atomicCAS), parents, logs.  The next window starts at iteration k0 + f with a fresh snapshot, i.e. an iteration
+//   whose nearest node was inserted in its own window is simply expanded again one window later, in a full-width pass,
+//   instead of being re-expanded by a single lane while the rest of the warp (and, through the lockstep barrier, of the
+//   CTA) waits.  Lane 0 has no predecessor in its window, so every window commits at least one iteration.
 // ---------------------------------------------------------------------------
 #ifndef TRRT_SCAN_AHEAD
 #define TRRT_SCAN_AHEAD 1024
@@ -523,9 +530,6 @@ __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE
 #ifndef TRRT_SPEC_LOCKSTEP
 #define TRRT_SPEC_LOCKSTEP 1
 #endif
-#ifndef TRRT_SPEC_PREDICT
-#define TRRT_SPEC_PREDICT 1 /* lane-parallel predicted re-expansions before the commit (phase A, part 3) */
-#endif
 #ifndef TRRT_SPEC_THREADS
 #define TRRT_SPEC_THREADS 384 /* measured on B200 (cfg 3, final kernel): 384 x 2 63.7 ms, 768 x 1 63.7 ms, 512 x 1 67.3 ms; see profiles/r1/NOTES.md */
 #endif
@@ -548,14 +552,15 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
     const int K = a.K;
     __shared__ __align__(16) double2 scan_tiles[(G == 32) ? (TRRT_SPEC_THREADS / 32) * 4 * TRRT_TILE_PAIRS : 1];
     double2 *scan_tile = scan_tiles + ((G == 32) ? (threadIdx.x >> 5) * 4 * TRRT_TILE_PAIRS : 0);
+    const unsigned lane_lt = (1u << g.gl) - 1u;
     // persistent groups: queries differ a lot in length (27% of the cfg-3 queries end early), so each group
     // pulls the next query from a counter instead of owning a fixed one.  One loop trip = one window.
     bool have = false, drained = false;
     int64_t q = 0;
     RrtQuery Q;
-    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0}; // scan is kept uniform; the others are lane-private sums, folded at the end
+    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0}; // lane-private sums, folded at the end
     int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND, iters = 0, k0 = 0;
-    TRRT_PROF(unsigned long long pf[24]; for (int i_ = 0; i_ < 24; i_++) pf[i_] = 0; long long t0_, t1_, t2_, t3_, t4_;)
+    TRRT_PROF(unsigned long long pf[24]; for (int i_ = 0; i_ < 24; i_++) pf[i_] = 0; long long t0_, t1_, t2_, t3_;)
     for (;;) {
         if (!have && !drained) {
             unsigned long long qq = 0;
@@ -572,14 +577,11 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         }
         // ---------------- phase A, part 1: sample, `qrand in G`, nearest scan
         TRRT_PROF(t0_ = clock64();)
-        const int n0 = n;
         int pre = TRRT_IT_NOT_RUN; // TRRT_IT_QRAND_BLOCKED, TRRT_IT_NOT_RUN (beyond the last iteration / no query) or -1 = live
         bool q_in_tree = false;    // rrt.py:151 against the snapshot (+ nodes of this window, folded in below)
         int near = -1, exist = -1; // nearest node; index of a tree node equal to qnew, or -1
         int islot = 0;             // where the index lookup of qnew ended (see tree_find_slot)
         double bd = INFINITY, qx = 0, qy = 0, qth = 0;
-        double wbest = INFINITY;   // squared distance to the nearest node inserted earlier in this window
-        int widx = -1;
         unsigned long long probes = 0;
         Expand e;
         e.code = TRRT_IT_NOT_RUN; e.flags = 0; e.lospx = e.arcpx = e.arcang = e.drive = 0;
@@ -597,8 +599,8 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         const bool live = (pre == -1) && !q_in_tree;
         if (have) {
             // the scan is executed by the whole warp (lanes without a live sample run through it with a dummy point)
-            if (G == 32) nearest_staged(scan_tile, Q.nx, Q.ny, n0, qx, qy, bd, near);
-            else nearest_private(Q.nx, Q.ny, live ? n0 : 0, qx, qy, bd, near);
+            if (G == 32) nearest_staged(scan_tile, Q.nx, Q.ny, n, qx, qy, bd, near);
+            else nearest_private(Q.nx, Q.ny, live ? n : 0, qx, qy, bd, near);
         }
 #if TRRT_SPEC_LOCKSTEP
         // ---------------- CTA barrier: expansion code is entered together; also the exit test
@@ -614,168 +616,119 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
             expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
             if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
         }
+        c.probe += probes;
         g.sync();
         TRRT_PROF(t3_ = clock64(); { const unsigned long long s_ = t3_ - t2_; pf[3] += s_; pf[4] += s_ * s_ >> 10; })
-        // ---------------- phase A, part 3: predicted re-expansions, lane-parallel
-        // A lane whose nearest node will be a node of its own window has to expand again from that node.  Doing that
-        // inside the serial commit costs one full expansion per such lane (0.92 per window on cfg 3, up to 4-5), with
-        // the other 31 lanes and - through the lockstep barrier - the other warps of the CTA waiting.  The candidates are
-        // known now: assume every lane whose tentative outcome inserts a node commits exactly that node; then lane j's
-        // nearest window node is the first strict minimum over the tentative nodes of the lanes before it.  All
-        // predicted lanes expand from their predicted node together (e2); the commit verifies the assumption (the
-        // node that is really nearest was inserted by the predicted lane from its tentative outcome) and falls back to
-        // the serial expansion otherwise.
-        bool has2 = false;
-        int pred = -1, pred_idx = -2, exist2 = -1, islot2 = 0;
-        Expand e2;
-        if (G > 1 && TRRT_SPEC_PREDICT) {
-            const bool will_insert = live && e.code == EX_ACCEPT && exist < 0 && !(e.flags & 2);
-            unsigned ins = g.ballot(will_insert);
-            double pbest = bd;
-            ins &= ~(1u << (G - 1)); // nobody comes after the last lane
-            while (ins) {
-                const int i = __ffs(ins) - 1;
-                ins &= ins - 1;
-                const double vx = g.bcast(e.wx, i), vy = g.bcast(e.wy, i);
-                const double dx = qx - vx, dy = qy - vy;
-                const double d = dx * dx + dy * dy;
-                if (g.gl > i && d < pbest) { pbest = d; pred = i; }
+        // ---------------- pass: fold the new nodes forward, find the first lane that has to start over
+        unsigned done = 0; // lanes whose outcome inserts a node
+        int fs;            // first lane that does not commit in this window
+        {
+            bool moved = false; // a node of this window is strictly nearer than the snapshot winner
+            int last = -1;
+            for (;;) {
+                const bool livel = pre == -1 && !q_in_tree;
+                const bool stop = pre == TRRT_IT_NOT_RUN || (livel && moved);
+                const bool insl = g.gl > last && livel && !moved && e.code == EX_ACCEPT && exist < 0;
+                const unsigned sm = g.ballot(stop), im = g.ballot(insl);
+                fs = sm ? __ffs(sm) - 1 : G;
+                const int ni = im ? __ffs(im) - 1 : G;
+                if (ni >= fs) break;
+                const int idx_i = n + __popc(done);
+                done |= 1u << ni;
+                last = ni;
+                const double vx = g.bcast(e.wx, ni), vy = g.bcast(e.wy, ni), vth = g.bcast(e.wth, ni);
+                if (g.gl > ni) {
+                    const double dx = qx - vx, dy = qy - vy;
+                    const double d = dx * dx + dy * dy;
+                    if (d < bd) moved = true;
+                    if (qx == vx && qy == vy && qth == vth) q_in_tree = true;                       // rrt.py:151
+                    if (exist < 0 && e.wx == vx && e.wy == vy && e.wth == vth) exist = idx_i;        // rrt.py:179
+                }
             }
-            has2 = live && pred >= 0;
-            const int src = has2 ? pred : g.gl;
-            const double ox = g.bcast(e.wx, src), oy = g.bcast(e.wy, src), oth = g.bcast(e.wth, src);
-            if (has2) {
-                expand_from<1>(solo, Q.m, a.P, ox, oy, oth, qx, qy, qth, Q.gx, Q.gy, Q.gth, e2);
-                if (e2.code == EX_ACCEPT) exist2 = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e2.wx, e2.wy, e2.wth, probes, islot2);
-            }
-            g.sync();
-            TRRT_PROF({ const unsigned m_ = g.ballot(has2); if (m_) { pf[11]++; pf[12] += __popc(m_); } })
         }
-        TRRT_PROF(t4_ = clock64(); { const unsigned long long s_ = t4_ - t3_; pf[5] += s_; pf[6] += s_ * s_ >> 10; })
-        // ---------------- phase B: commit in iteration order
-        bool running = true;
-        // what a step needs from its lane travels in ONE word (the commit loop is a serial chain of shuffles):
-        // pre (2 bits) | qrand in tree | a node of the window is nearer | outcome (2 bits) | qnew in tree | flags << 8
-        auto pack_static = [&]() {
-            const int p2 = (pre == -1) ? 0 : (pre == TRRT_IT_QRAND_BLOCKED ? 1 : 2);
-            const int oc = (e.code == EX_ACCEPT) ? 0 : (e.code == TRRT_IT_ARC_BLOCKED ? 1 : (e.code == TRRT_IT_STEER_CONSTRAINT ? 2 : 3));
-            return p2 | (oc << 4) | (e.flags << 8);
-        };
-        int word0 = pack_static();
-        for (int j = 0; j < G; j++) {
-            const int it = k0 + j;
-            int wj = g.bcast(word0 | ((int)q_in_tree << 2) | ((int)(wbest < bd) << 3) | ((int)(exist >= 0) << 6), j);
-            if ((wj & 3) == 2) break; // TRRT_IT_NOT_RUN: beyond the last iteration
-            int code = ((wj & 3) == 1) ? (int)TRRT_IT_QRAND_BLOCKED : -1, near_j = -1, newi = -1;
-            bool go = true;
-            if ((wj & 3) == 0) {
-                if (wj & 4) code = TRRT_IT_QRAND_IN_TREE; // rrt.py:151
+        // a lane before fs that ends the query: the reference raises (Q7), or the goal test passes (rrt.py:191-201)
+        bool finished = false;
+        int end = fs;
+        {
+            const bool livel = pre == -1 && !q_in_tree;
+            const unsigned tm = g.ballot(livel && ((e.flags & 2) || (e.code == EX_ACCEPT && (e.flags & 4)))) & ((fs >= 32) ? 0xffffffffu : ((1u << fs) - 1u));
+            if (tm) {
+                const int t = __ffs(tm) - 1;
+                end = t + 1;
+                done &= (end >= 32) ? 0xffffffffu : ((1u << end) - 1u);
+                finished = true;
+            }
+        }
+        // ---------------- commit: lanes [0, end) write their results together
+        {
+            const bool inseg = g.gl < end;
+            const bool livel = inseg && pre == -1 && !q_in_tree;
+            const int nl = (livel && e.code != TRRT_IT_STEER_CONSTRAINT) ? ((e.flags >> 4) & 3) : 0; // rays of this iteration
+            const unsigned m1 = g.ballot(nl >= 1), m2 = g.ballot(nl >= 2);
+            int code = TRRT_IT_NOT_RUN, near_j = -1, newi = -1;
+            bool edge = false; // this lane records an edge: cameFrom[newi] = (near, u)  (rrt.py:187-188)
+            if (inseg) {
+                if (pre != -1) code = TRRT_IT_QRAND_BLOCKED;        // rrt.py:148
+                else if (q_in_tree) code = TRRT_IT_QRAND_IN_TREE;  // rrt.py:151
                 else {
-                    const bool moved = (wj & 8) != 0; // lane j does not commit its tentative outcome
-                    if (moved) {
-                        // a node of this window is strictly nearer: lane j's iteration starts from it.  Either that is
-                        // the node it was expanded from ahead of time (part 3), or lane j redoes the expansion now.
-                        const bool hit = g.bcast((int)(has2 && widx == pred_idx), j) != 0;
-                        if (!hit) {
-                            // Not foreseen (typically: the node comes from a lane that itself moved).  The nodes of the
-                            // steps before j are final, so every lane from j on whose nearest node so far is one of
-                            // them, and which holds no expansion from it, expands now, together with lane j; lanes still
-                            // waiting for the node of a later lane (pred > j) keep their prediction.
-                            g.sync(); // nodes written by earlier steps are visible
-                            const bool need = g.gl >= j && pre == -1 && !q_in_tree && wbest < bd && !(has2 && (pred_idx == widx || pred > j));
-                            TRRT_PROF({ pf[14]++; pf[15] += __popc(g.ballot(need)); })
-                            if (need) {
-                                expand_from<1>(solo, Q.m, a.P, Q.nx[widx], Q.ny[widx], Q.nth[widx], qx, qy, qth, Q.gx, Q.gy, Q.gth, e2);
-                                exist2 = -1;
-                                if (e2.code == EX_ACCEPT) exist2 = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e2.wx, e2.wy, e2.wth, probes, islot2);
-                                has2 = true; pred = -1; pred_idx = widx;
-                            }
-                        } else { TRRT_PROF(pf[13]++;) }
-                        if (g.gl == j) {
-                            near = widx;
-                            e = e2; exist = exist2; islot = islot2;
-                            word0 = pack_static();
-                        }
-                        wj = g.bcast(word0 | ((int)(exist >= 0) << 6), j);
-                    }
-                    near_j = near; // only lane j itself uses it (its own edge record and log entry)
-                    const int oc = (wj >> 4) & 3, eflags = wj >> 8;
-                    const bool mine = g.gl == j;
-                    if (a.counters) { c.scan += (unsigned long long)n; if (mine) c.steer++; }
-                    if (oc == 2) code = TRRT_IT_STEER_CONSTRAINT;
+                    near_j = near;
+                    const int before = __popc(done & lane_lt); // nodes inserted by the earlier lanes of the window
+                    if (a.counters) { c.scan += (unsigned long long)(n + before); c.steer++; }
+                    if (e.code == TRRT_IT_STEER_CONSTRAINT) code = TRRT_IT_STEER_CONSTRAINT; // rrt.py:166
                     else {
-                        const int nl = (eflags >> 4) & 3;
-                        if (mine) {
-                            if (Q.los_log) {
-                                if (nl >= 1) Q.los_log[nlos] = (eflags >> 6) & 1;
-                                if (nl >= 2) Q.los_log[nlos + 1] = (eflags >> 7) & 1;
-                            }
-                            if (a.counters) { c.los += nl; c.lospx += e.lospx; c.arcpx += e.arcpx; c.arcang += e.arcang; c.drive += e.drive; }
+                        if (Q.los_log) {
+                            const int pos = nlos + __popc(m1 & lane_lt) + __popc(m2 & lane_lt);
+                            if (nl >= 1) Q.los_log[pos] = (e.flags >> 6) & 1;
+                            if (nl >= 2) Q.los_log[pos + 1] = (e.flags >> 7) & 1;
                         }
-                        nlos += nl;
-                        if (eflags & 2) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; code = TRRT_IT_NOT_RUN; go = false; }
-                        else if (oc == 1) code = TRRT_IT_ARC_BLOCKED;
-                        else { // rrt.py:179-201
-                            int idx = (wj & 64) ? g.bcast(exist, j) : -1; // `qnew in G` (rare): the node it equals
-                            if (idx < 0) {
-                                if (n >= K) { status = TRRT_ERR_CAPACITY; code = TRRT_IT_NOT_RUN; go = false; }
-                                else {
-                                    idx = n++;
-                                    code = TRRT_IT_NEW_NODE;
-                                    if (mine) {
-                                        Q.nx[idx] = e.wx; Q.ny[idx] = e.wy; Q.nth[idx] = e.wth;
-                                        tree_insert_from(Q.tab, Q.tmask, islot, idx); // parent / u follow below (a new node is never its own nearest)
-                                    }
-                                    // every lane folds the new node into its window minimum and equality flags
-                                    const double vx = g.bcast(e.wx, j), vy = g.bcast(e.wy, j), vth = g.bcast(e.wth, j);
-                                    if (g.gl > j) {
-                                        const double dx = qx - vx, dy = qy - vy;
-                                        const double d = dx * dx + dy * dy;
-                                        if (d < wbest) { wbest = d; widx = idx; }
-                                        if (qx == vx && qy == vy && qth == vth) q_in_tree = true;
-                                        if (exist < 0 && e.wx == vx && e.wy == vy && e.wth == vth) exist = idx;
-                                        if (has2) {
-                                            if (pred == j) pred_idx = moved ? -2 : idx; // the node part 3 assumed, or another one
-                                            if (exist2 < 0 && e2.wx == vx && e2.wy == vy && e2.wth == vth) exist2 = idx;
-                                        }
-                                    }
-                                }
-                            } else code = TRRT_IT_EXISTING_NODE;
-                            if (go) {
-                                newi = idx;
-                                if (idx != near_j && mine) { // rrt.py:187-188
-                                    Q.parent[idx] = near_j;
-                                    if (Q.uo) {
-                                        const bool st = eflags & 1;
-                                        Q.uo[5 * idx] = e.usteer; Q.uo[5 * idx + 1] = st ? NAN : e.iccx; Q.uo[5 * idx + 2] = st ? NAN : e.iccy;
-                                        Q.uo[5 * idx + 3] = st ? NAN : e.rad; Q.uo[5 * idx + 4] = e.udist;
-                                    }
-                                }
-                                if (eflags & 4) { sol = idx; status = TRRT_OK_FOUND; go = false; }
-                            }
+                        if (a.counters) { c.los += nl; c.lospx += e.lospx; c.arcpx += e.arcpx; c.arcang += e.arcang; c.drive += e.drive; }
+                        if (e.flags & 2) code = TRRT_IT_NOT_RUN;                              // rrt.py:170-171 raises
+                        else if (e.code == TRRT_IT_ARC_BLOCKED) code = TRRT_IT_ARC_BLOCKED;   // rrt.py:174
+                        else if (exist >= 0) { code = TRRT_IT_EXISTING_NODE; newi = exist; edge = newi != near; } // rrt.py:179 false
+                        else { // rrt.py:179-180: a new vertex
+                            newi = n + before;
+                            code = TRRT_IT_NEW_NODE;
+                            edge = true; // its nearest node is an older one
+                            Q.nx[newi] = e.wx; Q.ny[newi] = e.wy; Q.nth[newi] = e.wth;
+                            tree_insert_cas(Q.tab, Q.tmask, islot, newi);
                         }
                     }
                 }
-            }
-            if (g.gl == j) {
+                const int it = k0 + g.gl;
                 if (Q.it_near) Q.it_near[it] = near_j;
                 if (Q.it_new) Q.it_new[it] = newi;
                 if (Q.it_code) Q.it_code[it] = (uint8_t)code;
             }
-            iters = it + 1;
-            if (!go) {
-                if (status != TRRT_OK_FOUND) iters = it; // the iteration that raises is not counted
-                running = false;
-                break;
+            // cameFrom[qnew] is overwritten by every later edge to the same node (rrt.py:188; equal qnew are common: a
+            // clamped steer over the maximum distance depends only on the nearest node and the turn direction), so of the
+            // lanes of the window that target one node the last one writes
+            if (G > 1) {
+                const unsigned peers = __match_any_sync(g.mask, edge ? newi : ~(int)(threadIdx.x & 31));
+                if (edge && (peers >> (threadIdx.x & 31)) > 1u) edge = false; // a later lane records its edge to the same node
             }
+            if (edge) {
+                Q.parent[newi] = near;
+                if (Q.uo) {
+                    const bool st = e.flags & 1;
+                    Q.uo[5 * newi] = e.usteer; Q.uo[5 * newi + 1] = st ? NAN : e.iccx; Q.uo[5 * newi + 2] = st ? NAN : e.iccy;
+                    Q.uo[5 * newi + 3] = st ? NAN : e.rad; Q.uo[5 * newi + 4] = e.udist;
+                }
+            }
+            nlos += __popc(m1) + __popc(m2);
+            n += __popc(done);
+            iters = k0 + end;
+            if (finished) {
+                if (g.bcast(e.flags & 2, end - 1)) { status = TRRT_ERR_REF_RAISES_DRIVE_NONE; iters = k0 + end - 1; } // the iteration that raises is not counted
+                else { sol = g.bcast(newi, end - 1); status = TRRT_OK_FOUND; }
+            }
+            TRRT_PROF({ pf[16]++; pf[17] += end; })
         }
-        c.probe += probes;
         g.sync(); // tree and index writes of this window are visible to every lane's next phase A
-        TRRT_PROF({ const unsigned long long s_ = clock64() - t4_; pf[7] += s_; pf[8] += s_ * s_ >> 10; const unsigned long long w_ = clock64() - t2_; pf[9] += w_ * w_ >> 10; })
-        k0 += G;
-        if (!running || k0 >= K - 1) { // query finished
+        TRRT_PROF({ const unsigned long long s_ = clock64() - t3_; pf[7] += s_; pf[8] += s_ * s_ >> 10; const unsigned long long w_ = clock64() - t2_; pf[9] += w_ * w_ >> 10; })
+        k0 += end;
+        if (finished || k0 >= K - 1) { // query finished
             if (a.counters) { // fold the lane-private counters
-                c.los = g.sum(c.los); c.lospx = g.sum(c.lospx); c.arcpx = g.sum(c.arcpx); c.arcang = g.sum(c.arcang);
+                c.scan = g.sum(c.scan); c.los = g.sum(c.los); c.lospx = g.sum(c.lospx); c.arcpx = g.sum(c.arcpx); c.arcang = g.sum(c.arcang);
                 c.steer = g.sum(c.steer); c.drive = g.sum(c.drive); c.probe = g.sum(c.probe);
             }
             rrt_finish<G>(a, q, g, Q, K, iters, n, sol, status, nlos, c);
