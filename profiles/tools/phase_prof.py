@@ -35,13 +35,16 @@ lib.trrt_debug_phase_prof(buf)
 v = [int(x) for x in buf]
 W = v[10]
 print(f"kernel {a.elapsed_time(b):.2f} ms, windows (warp x window) {W}, iterations {int(r.iters.sum())}")
-names = [("scan (to barrier arrival)", 0, 1), ("barrier wait", 2, None), ("expansion", 3, 4), ("pass + commit", 7, 8)]
-tot = v[0] + v[2] + v[3] + v[5] + v[7]
+names = [("sample, publish", 19, None), ("wait at barrier 1", 18, None), ("pooled scan", 0, 1), ("wait at barrier 2", 2, None), ("expansion", 3, 4), ("pass + commit", 7, 8)]
+WR = v[20] or W  # warp-rounds (idle warps take part in the pooled scan and the barriers)
+print(f"warp-rounds {WR}, of which with a query {W}")
+tot = v[0] + v[2] + v[3] + v[5] + v[7] + v[18] + v[19]
 for nm, i, j in names:
-    mean = v[i] / W
+    Wn = W if i in (3, 7) else WR
+    mean = v[i] / Wn
     line = f"  {nm:28s} mean {mean:9.0f} cycles  {100 * v[i] / tot:5.1f}%"
     if j is not None:
-        var = v[j] * 1024 / W - mean * mean
+        var = v[j] * 1024 / Wn - mean * mean
         line += f"  std {max(var, 0) ** 0.5:9.0f}"
     print(line)
 post = (v[3] + v[7]) / W

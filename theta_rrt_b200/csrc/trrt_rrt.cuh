@@ -125,7 +125,7 @@ struct Expand {
 };
 
 #ifndef TRRT_EXPAND_INLINE
-#define TRRT_EXPAND_INLINE __noinline__ /* measured: inlining it (Expand in registers) 71.8 ms vs 70.2 ms as a call */
+#define TRRT_EXPAND_INLINE __forceinline__ /* one call site per kernel; measured on cfg 3: inlined 38.8 ms, as a call 39.4 ms */
 #endif
 // Everything after the nearest node is known.  GA lanes share the rays / raster; GA == 1 is one lane working
 // alone (speculative schedule) and takes the single-lane code of trrt_lane.cuh.
@@ -469,15 +469,16 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+// Nodes [lo, n) of the tree (lo = 0: the whole tree); lowest index on ties inside the range.
 __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE_PAIRS] of this warp */, const double *__restrict__ nx,
-                                               const double *__restrict__ ny, int n, double qx, double qy, double &bd_out, int &bi_out) {
+                                               const double *__restrict__ ny, int lo, int n, double qx, double qy, double &bd_out, int &bi_out) {
     const int lane = threadIdx.x & 31;
     double bd = INFINITY;
     int bi = 0x7fffffff;
-    int i = 0;
+    int i = lo;
 #define TRRT_NODE(xv, yv, idx) { double dx = qx - (xv), dy = qy - (yv); double d = dx * dx + dy * dy; if (d < bd) { bd = d; bi = (idx); } }
     if ((((uintptr_t)nx ^ (uintptr_t)ny) & 15) == 0) { // rows equally aligned
-        if (((uintptr_t)nx & 15) != 0 && n > 0) { TRRT_NODE(nx[0], ny[0], 0); i = 1; }
+        if (((uintptr_t)(nx + i) & 15) != 0 && i < n) { TRRT_NODE(nx[i], ny[i], i); i++; }
         const double2 *x2 = reinterpret_cast<const double2 *>(nx + i);
         const double2 *y2 = reinterpret_cast<const double2 *>(ny + i);
         const int pairs = (n - i) >> 1;
@@ -531,7 +532,9 @@ __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE
 #define TRRT_SPEC_LOCKSTEP 1
 #endif
 #ifndef TRRT_SPEC_THREADS
-#define TRRT_SPEC_THREADS 384 /* measured on B200 (cfg 3, final kernel): 384 x 2 63.7 ms, 768 x 1 63.7 ms, 512 x 1 67.3 ms; see profiles/r1/NOTES.md */
+#define TRRT_SPEC_THREADS 448 /* 2 CTAs of 14 warps = 28 warps per SM at 72 registers: the 4 096 queries of cfg 3 are resident at once
+                                 (4 144 warps), no second wave.  Measured on B200 (cfg 3): 448 x 2 39.4 ms, 384 x 2 43.9 ms, 512 x 2 (64
+                                 registers) 42.4 ms, 768 x 1 43.0 ms; see profiles/r2/NOTES.md */
 #endif
 #ifndef TRRT_SPEC_BLOCKS_PER_SM
 #define TRRT_SPEC_BLOCKS_PER_SM 2
@@ -552,6 +555,14 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
     const int K = a.K;
     __shared__ __align__(16) double2 scan_tiles[(G == 32) ? (TRRT_SPEC_THREADS / 32) * 4 * TRRT_TILE_PAIRS : 1];
     double2 *scan_tile = scan_tiles + ((G == 32) ? (threadIdx.x >> 5) * 4 * TRRT_TILE_PAIRS : 0);
+    // pooled scan (G == 32): what every warp of the CTA needs to scan a slice of any warp's tree for that warp's samples
+    constexpr int NW = TRRT_SPEC_THREADS / 32;
+    static_assert(NW <= 32, "one lane per warp of the CTA in the scan partition");
+    __shared__ double2 pool_q[(G == 32) ? NW : 1][32];            // sample of lane l of warp w
+    __shared__ const double *pool_x[(G == 32) ? NW : 1], *pool_y[(G == 32) ? NW : 1];
+    __shared__ int pool_n[(G == 32) ? NW : 1];                    // nodes to scan (0: warp w has nothing to scan)
+    __shared__ double pool_d[(G == 32) ? 2 * NW : 1][32];         // partial minima: one slot per (warp, tree) overlap
+    __shared__ int pool_i[(G == 32) ? 2 * NW : 1][32];
     const unsigned lane_lt = (1u << g.gl) - 1u;
     // persistent groups: queries differ a lot in length (27% of the cfg-3 queries end early), so each group
     // pulls the next query from a counter instead of owning a fixed one.  One loop trip = one window.
@@ -560,7 +571,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
     RrtQuery Q;
     RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0}; // lane-private sums, folded at the end
     int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND, iters = 0, k0 = 0;
-    TRRT_PROF(unsigned long long pf[24]; for (int i_ = 0; i_ < 24; i_++) pf[i_] = 0; long long t0_, t1_, t2_, t3_;)
+    TRRT_PROF(unsigned long long pf[24]; for (int i_ = 0; i_ < 24; i_++) pf[i_] = 0; long long t0_, t1_ = 0, t2_, t3_, t4_ = 0, t5_ = 0;)
     for (;;) {
         if (!have && !drained) {
             unsigned long long qq = 0;
@@ -597,20 +608,77 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
             }
         }
         const bool live = (pre == -1) && !q_in_tree;
-        if (have) {
-            // the scan is executed by the whole warp (lanes without a live sample run through it with a dummy point)
-            if (G == 32) nearest_staged(scan_tile, Q.nx, Q.ny, n, qx, qy, bd, near);
-            else nearest_private(Q.nx, Q.ny, live ? n : 0, qx, qy, bd, near);
-        }
+        // ---------------- nearest scan.  One warp per query (G == 32): the trees of a CTA's queries differ in size, some
+        // warps have no query any more, and the expansion below is entered by the whole CTA together -- so the CTA scans
+        // as a pool.  The trees are cut into tiles of 2 * TRRT_TILE_PAIRS nodes, the tiles of all trees are laid end to end
+        // and every warp takes an equal share of that list (a share overlaps one tree or a few); for each overlap the warp
+        // scans its slice for the 32 samples of the warp that owns the tree and leaves the partial minima in shared
+        // memory; after the barrier the owner folds the partials of its tree in node order (lowest index on ties).
+        int part0 = 0, nparts = 0; // this warp's tree: first partial slot, number of partials
+        if (G == 32) {
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            const bool scan_me = have && g.any(live);
+            pool_q[wid][lane] = make_double2(qx, qy);
+            if (lane == 0) { pool_n[wid] = scan_me ? n : 0; pool_x[wid] = Q.nx; pool_y[wid] = Q.ny; }
+            TRRT_PROF(t1_ = clock64();)
+            __syncthreads();
+            TRRT_PROF(t4_ = clock64();)
+            // lane v describes the tree of warp v: tiles, first tile in the list, first / last warp that scans it, first slot
+            constexpr int TN = 2 * TRRT_TILE_PAIRS;
+            const int nv = lane < NW ? pool_n[lane] : 0;
+            const int tv = (nv + TN - 1) / TN;
+            int cv = tv; // inclusive prefix sum of the tile counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, cv, o); if (lane >= o) cv += t; }
+            const int T = __shfl_sync(0xffffffffu, cv, 31);
+            cv -= tv; // first tile of tree v
+            // warp k owns tiles [k*T/NW, (k+1)*T/NW): tile c belongs to warp ((c+1)*NW - 1) / T
+            int kf = 0, kl = -1;
+            if (tv > 0) { kf = ((cv + 1) * NW - 1) / T; kl = ((cv + tv) * NW - 1) / T; }
+            const int npv = kl - kf + 1;
+            int bv = npv; // exclusive prefix sum: first partial slot of tree v
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, bv, o); if (lane >= o) bv += t; }
+            bv -= npv;
+            part0 = __shfl_sync(0xffffffffu, bv, wid);
+            nparts = __shfl_sync(0xffffffffu, npv, wid);
+            if (T > 0) {
+                const int a0 = (wid * T) / NW, a1 = ((wid + 1) * T) / NW; // this warp's share of the tile list
+                // (a warp whose share is empty, T < NW, still owes its slot: it leaves +inf there)
+                unsigned todo = __ballot_sync(0xffffffffu, tv > 0 && kf <= wid && wid <= kl);
+                while (todo) {
+                    const int v = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int c0 = __shfl_sync(0xffffffffu, cv, v), tc = __shfl_sync(0xffffffffu, tv, v);
+                    const int n_v = __shfl_sync(0xffffffffu, nv, v), k0v = __shfl_sync(0xffffffffu, kf, v), b0 = __shfl_sync(0xffffffffu, bv, v);
+                    const int t0 = (a0 > c0 ? a0 : c0) - c0, t1 = (a1 < c0 + tc ? a1 : c0 + tc) - c0;
+                    const int lo = t0 * TN, hi = t1 * TN < n_v ? t1 * TN : n_v;
+                    const double2 sq = pool_q[v][lane];
+                    double pd = INFINITY;
+                    int pi = 0x7fffffff;
+                    if (lo < hi) nearest_staged(scan_tile, pool_x[v], pool_y[v], lo, hi, sq.x, sq.y, pd, pi);
+                    const int slot = b0 + (wid - k0v);
+                    pool_d[slot][lane] = pd; pool_i[slot][lane] = pi;
+                }
+            }
+        } else if (have) nearest_private(Q.nx, Q.ny, live ? n : 0, qx, qy, bd, near);
 #if TRRT_SPEC_LOCKSTEP
-        // ---------------- CTA barrier: expansion code is entered together; also the exit test
-        TRRT_PROF(t1_ = clock64();)
+        // ---------------- CTA barrier: the partial minima are complete, the expansion code is entered together; also the exit test
+        TRRT_PROF(t5_ = clock64();)
         if (!__syncthreads_or(have ? 1 : 0)) break;
-        TRRT_PROF(t2_ = clock64(); if (have) { const unsigned long long s_ = t1_ - t0_; pf[0] += s_; pf[1] += s_ * s_ >> 10; pf[2] += t2_ - t1_; pf[10]++; })
+        TRRT_PROF(t2_ = clock64(); { const unsigned long long s_ = t5_ - t4_; pf[0] += s_; pf[1] += s_ * s_ >> 10; pf[2] += t2_ - t5_; pf[18] += t4_ - t1_; pf[19] += t1_ - t0_; pf[20]++; if (have) pf[10]++; })
         if (!have) continue;
 #else
-        if (!have) break; // no query left for this group
+        if (G == 32) { if (!__syncthreads_or(have ? 1 : 0)) break; if (!have) continue; }
+        else if (!have) break; // no query left for this group
 #endif
+        if (G == 32) { // fold the partial minima of this warp's tree, in node order: the first minimum wins
+            const int lane = threadIdx.x & 31;
+            for (int j = 0; j < nparts; j++) {
+                const double d = pool_d[part0 + j][lane];
+                if (d < bd) { bd = d; near = pool_i[part0 + j][lane]; }
+            }
+        }
         // ---------------- phase A, part 2: everything after the nearest node
         if (live) {
             expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
