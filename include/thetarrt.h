@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TRRT_VERSION 100 /* 0.1.0 */
+#define TRRT_VERSION 200 /* 0.2.0 */
 
 /* Parameters the reference keeps in `builtins` (main.py:15-32). */
 typedef struct trrt_params {
@@ -158,13 +158,12 @@ typedef struct trrt_rrt_args {
     int64_t n_queries;
     int32_t K;
     int32_t lanes_per_query; /* 0 = auto; else 1,2,4,8,16,32 */
-    int32_t schedule;        /* 0 = speculative window of `lanes` iterations in one persistent kernel (default),
-                                1 = cooperative per iteration, 2 = the window of 32 iterations as three kernels per
-                                window over all queries (lanes must be 0 or 32); all give identical results */
-    int32_t reserved0;
+    int32_t schedule;        /* 0 = speculative window of up to `lanes` iterations in one persistent kernel (default),
+                                1 = cooperative, one iteration at a time; both give identical results */
+    int32_t sample_xy_i16;   /* 0: d_sample_xy is int32 [n_queries][K-1][2]; 1: int16 [n_queries][K-1][2] (coordinates fit: side <= 32768) */
     const double *d_start;   /* [n_queries][3] = x, y, theta_deg (rrt.py:132) */
     const double *d_goal;    /* [n_queries][3]                    (rrt.py:133) */
-    const int32_t *d_sample_xy; /* [n_queries][K-1][2]  rand_conf xy (rrt.py:144) */
+    const void *d_sample_xy;    /* [n_queries][K-1][2]  rand_conf xy (rrt.py:144), int32 or int16 (sample_xy_i16) */
     const double *d_sample_th;  /* [n_queries][K-1]     rand_conf theta          */
     /* tree outputs, node index = insertion order of G (rrt.py:134-136,180) */
     double *d_node_x;  /* [n_queries][K] */
@@ -186,23 +185,25 @@ typedef struct trrt_rrt_args {
     /* scratch */
     void *d_work;
     size_t work_bytes; /* >= trrt_rrt_workspace_bytes(n_queries, K) */
+    /* Optional packed copy of the trees (all NULL to skip).  The tree arrays above are [n_queries][K] blocks of which
+       only the first n_nodes[q] rows exist (G and cameFrom as rrt.rrt returns them, rrt.py:204-206; about half of K on
+       the benchmark workload).  When d_row_start is given, a query that finishes reserves n_nodes[q] consecutive rows of
+       the packed arrays with one atomic add on *d_pack_rows and copies its rows there; d_row_start[q] is its first row.
+       The caller sets *d_pack_rows to the first row to use before the call (0, or the row where this call's block starts
+       inside larger arrays); afterwards it holds the row behind the last one, so the rows of a batch travel to the host
+       as ONE linear copy per array.  Queries land in completion order, so row_start is not monotone in q.
+       Rows used by a call: sum of n_nodes, at most n_queries * K. */
+    uint64_t *d_pack_rows;  /* [1]  next free row */
+    int64_t *d_row_start;   /* [n_queries] */
+    double *d_pack_x;       /* [rows] */
+    double *d_pack_y;
+    double *d_pack_th;
+    int32_t *d_pack_parent;
+    double *d_pack_u;       /* [rows][5]; NULL unless d_u is given too */
 } trrt_rrt_args;
 
 size_t trrt_rrt_workspace_bytes(int64_t n_queries, int32_t K);
 int trrt_rrt_batch(const trrt_rrt_args *args, void *stream);
-
-/* ---------------------------------------------------------------------------
- * Result packing of K2.  The tree arrays of trrt_rrt_batch are [n_queries][K]
- * blocks of which only the first n_nodes[q] rows exist (G, cameFrom as returned
- * by rrt.rrt, rrt.py:204-206).  This copies those rows, device to device, to
- * rows d_row_start[q] ... d_row_start[q] + n_nodes[q] - 1 of packed arrays
- * (d_pu: 5 values per row), so that the host side can fetch a batch as one
- * linear copy of the rows that exist.  d_row_start: int64 [n_queries], e.g. the
- * exclusive prefix sum of d_n_nodes.  d_u / d_pu may both be NULL.
- * ------------------------------------------------------------------------- */
-int trrt_rrt_pack_rows(int64_t n_queries, int32_t K, const int32_t *d_n_nodes, const int64_t *d_row_start, const double *d_node_x,
-                       const double *d_node_y, const double *d_node_th, const int32_t *d_parent, const double *d_u, double *d_px,
-                       double *d_py, double *d_pth, int32_t *d_pparent, double *d_pu, void *stream);
 
 /* ---------------------------------------------------------------------------
  * Single-step entry points (batches of independent inputs, one result each);

@@ -31,14 +31,14 @@ def test_library_exports_every_declared_symbol():
 
 def test_trivial_host_calls():
     lib = _lib.load()
-    assert lib.trrt_version() == 100
+    assert lib.trrt_version() == 200
     assert lib.trrt_grid_words(100, 100) == 400 and lib.trrt_grid_words(300, 300) == 3000
     assert lib.trrt_error_string(2).decode().startswith("map must be square")
     p = _lib.CParams()
     lib.trrt_default_params(C.byref(p))
     assert (p.thetastar, p.forwardonly, p.bikelength, p.leftconstraint, p.rightconstraint) == (1, 1, 5, -65, 65)
     assert (p.frontclearance, p.maxdrivedist, p.tol_xy, p.tol_ang, p.weightxy) == (2, 30, 10, 45, .6)
-    assert lib.trrt_rrt_workspace_bytes(4096, 5001) == 4096 * 16384 * 4 + 256 + (4096 * 32 * (17 * 4 + 20 * 8) + 4096 * (6 * 4 + 8 * 8) + 256)
+    assert lib.trrt_rrt_workspace_bytes(4096, 5001) == 4096 * 16384 * 4 + 256  # work counter + one index table per query
 
 
 def test_struct_layouts_match_header():

@@ -536,8 +536,11 @@ def test_rrt_host_valid_rows_only(maps):
             n = int(ref["n_nodes"][q])
             c = next(c for c in range(chunks) if nq * c // chunks <= q < nq * (c + 1) // chunks)
             lo = nq * c // chunks
-            assert rs[q] == lo * K + int(ref["n_nodes"][lo:q].sum()), q  # packed behind the earlier trees of its piece
+            hi = nq * (c + 1) // chunks
+            # inside the block of its piece (queries land in completion order), which is filled without gaps
+            assert lo * K <= rs[q] and rs[q] + n <= lo * K + int(ref["n_nodes"][lo:hi].sum()), q
             rows = slice(int(rs[q]), int(rs[q]) + n)
+            assert not touched[rows].any(), q  # no two trees overlap
             touched[rows] = True
             for k in ("node_x", "node_y", "node_theta"):
                 assert bits_equal(flat[k][rows, 0], ref[k][q, :n]), (k, q)
@@ -547,6 +550,23 @@ def test_rrt_host_valid_rows_only(maps):
         for k in ("node_x", "node_y", "node_theta", "u"):
             assert (flat[k][~touched] == SENT).all(), k
         assert (flat["parent"][~touched] == -777).all()
+    # `u` is opt-in: without it neither the copy nor the kernel's u rows exist
+    out2 = {k: v for k, v in out.items() if k != "u"}
+    for t in out2.values():
+        t.zero_()
+    p.rrt_host(*ins, out=out2, K=K, chunks=3, valid_rows_only=True)
+    torch.cuda.synchronize()
+    rs = out2["row_start"].numpy()
+    for q in range(nq):
+        n = int(ref["n_nodes"][q])
+        assert np.array_equal(out2["parent"].numpy().reshape(-1)[rs[q]:rs[q] + n], ref["parent"][q, :n])
+    # resident packed result of Planner.rrt
+    r = p.rrt(starts, goals, sxy, sth, K=K, pack=True).host()
+    assert int(r["pack_total"][0]) == int(ref["n_nodes"].sum())
+    for q in range(nq):
+        n, r0 = int(ref["n_nodes"][q]), int(r["row_start"][q])
+        assert bits_equal(r["pack_x"][r0:r0 + n], ref["node_x"][q, :n]) and np.array_equal(r["pack_parent"][r0:r0 + n], ref["parent"][q, :n])
+        assert np.array_equal(r["pack_u"][r0 + 1:r0 + n].view(np.int64), ref["u"][q, 1:n].view(np.int64))
     with pytest.raises(ValueError):
         bad = dict(out); bad["node_x"] = torch.zeros((nq, K), dtype=torch.float64)  # not pinned
         p.rrt_host(*ins, out=bad, K=K, chunks=2, valid_rows_only=True)

@@ -36,7 +36,7 @@ class CRrtArgs(C.Structure):
         ("d_bits", C.c_void_p), ("n_maps", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("d_map_id", C.c_void_p),
         ("params", CParams),
         ("n_queries", C.c_int64), ("K", C.c_int32), ("lanes_per_query", C.c_int32),
-        ("schedule", C.c_int32), ("reserved0", C.c_int32),
+        ("schedule", C.c_int32), ("sample_xy_i16", C.c_int32),
         ("d_start", C.c_void_p), ("d_goal", C.c_void_p), ("d_sample_xy", C.c_void_p), ("d_sample_th", C.c_void_p),
         ("d_node_x", C.c_void_p), ("d_node_y", C.c_void_p), ("d_node_th", C.c_void_p), ("d_parent", C.c_void_p),
         ("d_u", C.c_void_p), ("d_n_nodes", C.c_void_p), ("d_sol", C.c_void_p), ("d_status", C.c_void_p),
@@ -44,6 +44,8 @@ class CRrtArgs(C.Structure):
         ("d_it_near", C.c_void_p), ("d_it_new", C.c_void_p), ("d_it_code", C.c_void_p), ("d_los_log", C.c_void_p),
         ("d_n_los", C.c_void_p), ("d_counters", C.c_void_p),
         ("d_work", C.c_void_p), ("work_bytes", C.c_size_t),
+        ("d_pack_rows", C.c_void_p), ("d_row_start", C.c_void_p), ("d_pack_x", C.c_void_p), ("d_pack_y", C.c_void_p),
+        ("d_pack_th", C.c_void_p), ("d_pack_parent", C.c_void_p), ("d_pack_u", C.c_void_p),
     ]
 
 
@@ -80,7 +82,6 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "trrt_rrt_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "trrt_rrt_batch": (C.c_int, [C.POINTER(CRrtArgs), C.c_void_p]),
-    "trrt_rrt_pack_rows": (C.c_int, [C.c_int64, C.c_int32] + [C.c_void_p] * 13),
     "trrt_steer_batch": (C.c_int, [C.POINTER(CParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "trrt_drive_batch": (C.c_int, [C.POINTER(CParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "trrt_arc_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,

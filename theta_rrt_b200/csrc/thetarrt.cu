@@ -10,7 +10,6 @@
 //   rrt_kernel_spec<G>    K2: fused rrt.rrt loop, speculative window of G iterations, persistent (trrt_rrt.cuh)
 //   rrt_kernel_coop<G>        same loop, G lanes cooperating on one iteration at a time
 //   steer / drive / arc batch kernels: single steps of K2 for the drop-in helpers and step-level parity tests
-//   rrt_pack_rows_kernel      the tree rows of K2 that exist, packed for the transfer to the host
 //   findnearest_kernel    rrt.findnearest over the edge log
 //   theta_kernel<G>       K3: A* / lazy Theta*, G lanes per query, G-ary heap
 //
@@ -938,17 +937,22 @@ int trrt_rrt_batch(const trrt_rrt_args *args, void *stream) {
         !A.d_parent || !A.d_n_nodes || !A.d_sol || !A.d_status || !A.d_iters || !A.d_work)
         return TRRT_ERR_INVALID_ARGUMENT;
     if (A.d_los_log && !A.d_n_los) return TRRT_ERR_INVALID_ARGUMENT;
+    if (A.d_row_start && (!A.d_pack_rows || !A.d_pack_x || !A.d_pack_y || !A.d_pack_th || !A.d_pack_parent || (A.d_pack_u && !A.d_u)))
+        return TRRT_ERR_INVALID_ARGUMENT;
     if (A.work_bytes < trrt_rrt_workspace_bytes(A.n_queries, A.K)) return TRRT_ERR_WORKSPACE_TOO_SMALL;
     if ((uintptr_t)A.d_work & 7) return TRRT_ERR_INVALID_ARGUMENT;
+    if ((uintptr_t)A.d_sample_xy & (A.sample_xy_i16 ? 3 : 7)) return TRRT_ERR_INVALID_ARGUMENT; // read as short2 / int2
     int G = A.lanes_per_query != 0 ? A.lanes_per_query : 32; // one warp per query unless told otherwise
     RrtDev d;
     d.bits = A.d_bits; d.H = A.H; d.W = A.W; d.wpr = (A.W + 31) / 32; d.map_id = A.d_map_id; d.P = to_dev(A.params);
-    d.nq = A.n_queries; d.K = A.K; d.start = A.d_start; d.goal = A.d_goal; d.sxy = A.d_sample_xy; d.sth = A.d_sample_th;
+    d.nq = A.n_queries; d.K = A.K; d.start = A.d_start; d.goal = A.d_goal; d.sxy = (const int32_t *)A.d_sample_xy; d.sxy16 = A.sample_xy_i16 ? 1 : 0; d.sth = A.d_sample_th;
     d.nx = A.d_node_x; d.ny = A.d_node_y; d.nth = A.d_node_th; d.parent = A.d_parent; d.u = A.d_u;
     d.n_nodes = A.d_n_nodes; d.sol = A.d_sol; d.status = A.d_status; d.iters = A.d_iters;
     d.it_near = A.d_it_near; d.it_new = A.d_it_new; d.it_code = A.d_it_code; d.los_log = A.d_los_log; d.n_los = A.d_n_los;
     d.counters = (unsigned long long *)A.d_counters;
     d.next_query = (unsigned long long *)A.d_work;
+    d.pack_rows = (unsigned long long *)A.d_pack_rows; d.row_start = (long long *)A.d_row_start;
+    d.px = A.d_pack_x; d.py = A.d_pack_y; d.pth = A.d_pack_th; d.pparent = A.d_pack_parent; d.pu = A.d_pack_u;
     d.tab = (int32_t *)((char *)A.d_work + 256); d.tsize = rrt_tsize(A.K);
     cudaStream_t st = (cudaStream_t)stream;
     int threads = 128;
@@ -1029,46 +1033,6 @@ int trrt_arc_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
     case 32: arc_batch_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(d_bits, H, W, wpr, d_map_id, n, d_in, d_blocked); break;
     default: return TRRT_ERR_INVALID_ARGUMENT;
     }
-    CUDA_TRY(cudaGetLastError());
-    return TRRT_OK;
-}
-
-// ===========================================================================
-// packing of the tree rows that exist: query q's rows [0, n_nodes[q]) of the [n_queries][K] arrays of K2 go to rows
-// row_start[q] ... of packed arrays, so that a batch travels to the host as one linear copy of the valid rows (the
-// trees fill about half of their capacity on cfg 3).  One small CTA per query, grid-stride; device-to-device.
-// ===========================================================================
-__global__ void __launch_bounds__(128) rrt_pack_rows_kernel(int64_t nq, int K, const int32_t *__restrict__ n_nodes, const int64_t *__restrict__ row_start,
-                                                            const double *__restrict__ sx, const double *__restrict__ sy,
-                                                            const double *__restrict__ sth, const int32_t *__restrict__ sp,
-                                                            const double *__restrict__ su, double *__restrict__ ox, double *__restrict__ oy,
-                                                            double *__restrict__ oth, int32_t *__restrict__ op, double *__restrict__ ou) {
-    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
-        int n = __ldg(n_nodes + q);
-        n = n < 0 ? 0 : (n > K ? K : n);
-        const int64_t base = q * K, dst = __ldg(row_start + q);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            ox[dst + i] = sx[base + i];
-            oy[dst + i] = sy[base + i];
-            oth[dst + i] = sth[base + i];
-            op[dst + i] = sp[base + i];
-        }
-        if (su && ou)
-            for (int i = threadIdx.x; i < 5 * n; i += blockDim.x) ou[5 * dst + i] = su[5 * base + i];
-    }
-}
-
-int trrt_rrt_pack_rows(int64_t n_queries, int32_t K, const int32_t *d_n_nodes, const int64_t *d_row_start, const double *d_node_x,
-                       const double *d_node_y, const double *d_node_th, const int32_t *d_parent, const double *d_u, double *d_px, double *d_py,
-                       double *d_pth, int32_t *d_pparent, double *d_pu, void *stream) {
-    if (n_queries < 0 || K < 1) return TRRT_ERR_INVALID_ARGUMENT;
-    if (n_queries == 0) return TRRT_OK;
-    if (!d_n_nodes || !d_row_start || !d_node_x || !d_node_y || !d_node_th || !d_parent || !d_px || !d_py || !d_pth || !d_pparent)
-        return TRRT_ERR_INVALID_ARGUMENT;
-    if ((d_u == nullptr) != (d_pu == nullptr)) return TRRT_ERR_INVALID_ARGUMENT;
-    const int64_t cap = (int64_t)sm_count() * 4, blocks = n_queries < cap ? n_queries : cap;
-    rrt_pack_rows_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(n_queries, K, d_n_nodes, d_row_start, d_node_x, d_node_y, d_node_th, d_parent,
-                                                                            d_u, d_px, d_py, d_pth, d_pparent, d_pu);
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }

@@ -36,7 +36,8 @@ struct RrtDev {
     int64_t nq;
     int K;
     const double *start, *goal;
-    const int32_t *sxy;
+    const int32_t *sxy; // int32 pairs, or int16 pairs when sxy16 is set
+    int sxy16;
     const double *sth;
     double *nx, *ny, *nth;
     int32_t *parent;
@@ -49,6 +50,11 @@ struct RrtDev {
     int32_t *tab; // [nq][tsize] open-addressing index table for the `in G.keys()` tests
     int tsize;
     unsigned long long *next_query; // work counter of the persistent speculative kernel (zeroed by the launcher)
+    // optional packed copy of the rows that exist (see trrt_rrt_args in thetarrt.h)
+    unsigned long long *pack_rows;
+    long long *row_start;
+    double *px, *py, *pth, *pu;
+    int32_t *pparent;
 };
 
 __device__ __forceinline__ unsigned hash3(double x, double y, double t) {
@@ -245,7 +251,7 @@ __device__ __forceinline__ void rrt_ptrs(const RrtDev &a, int64_t q, RrtQuery &Q
     Q.nx = a.nx + q * K; Q.ny = a.ny + q * K; Q.nth = a.nth + q * K;
     Q.parent = a.parent + q * K;
     Q.uo = a.u ? a.u + q * (int64_t)K * 5 : nullptr;
-    Q.sxy = a.sxy + q * (int64_t)(K - 1) * 2;
+    Q.sxy = a.sxy + q * (int64_t)(K - 1) * (a.sxy16 ? 1 : 2);
     Q.sth = a.sth + q * (int64_t)(K - 1);
     Q.it_near = a.it_near ? a.it_near + q * (int64_t)(K - 1) : nullptr;
     Q.it_new = a.it_new ? a.it_new + q * (int64_t)(K - 1) : nullptr;
@@ -254,6 +260,17 @@ __device__ __forceinline__ void rrt_ptrs(const RrtDev &a, int64_t q, RrtQuery &Q
     Q.tab = a.tab + q * (int64_t)a.tsize;
     Q.tmask = a.tsize - 1;
     Q.gx = a.goal[3 * q]; Q.gy = a.goal[3 * q + 1]; Q.gth = standardangle(a.goal[3 * q + 2]);
+}
+
+// rand_conf's (x, y) of iteration `it` (rrt.py:144): int32 pairs, or int16 pairs (half the host-to-device bytes)
+__device__ __forceinline__ void sample_xy(const RrtDev &a, const RrtQuery &Q, int it, int &sx, int &sy) {
+    if (a.sxy16) {
+        const short2 v = __ldg(reinterpret_cast<const short2 *>(Q.sxy) + it);
+        sx = v.x; sy = v.y;
+    } else {
+        const int2 v = __ldg(reinterpret_cast<const int2 *>(Q.sxy) + it);
+        sx = v.x; sy = v.y;
+    }
 }
 
 // pointers + empty index + the start node (rrt.py:132-138)
@@ -305,6 +322,21 @@ __device__ __forceinline__ int rrt_insert(const Group<G> &g, const RrtQuery &Q, 
     return idx;
 }
 
+// n elements, G lanes, eight independent loads in flight per lane (the copy sits on the critical path of its CTA: the
+// other warps wait for this one at the next barrier)
+template <int G, typename T>
+__device__ __forceinline__ void group_copy(const Group<G> &g, T *__restrict__ dst, const T *__restrict__ src, int n) {
+    int i = g.gl;
+    for (; i + 7 * G < n; i += 8 * G) {
+        T v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = src[i + k * G];
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[i + k * G] = v[k];
+    }
+    for (; i < n; i += G) dst[i] = src[i];
+}
+
 struct RrtCounters {
     unsigned long long scan, los, lospx, arcpx, arcang, steer, drive, probe;
 };
@@ -330,6 +362,15 @@ __device__ __forceinline__ void rrt_finish(const RrtDev &a, int64_t q, const Gro
             unsigned long long *o = a.counters + q * 8;
             o[0] = c.scan; o[1] = c.los; o[2] = c.lospx; o[3] = c.arcpx; o[4] = c.arcang; o[5] = c.steer; o[6] = c.drive; o[7] = c.probe;
         }
+    }
+    if (a.row_start) { // packed copy of the rows that exist: one row reservation per query, coalesced copies by the group
+        unsigned long long r0 = 0;
+        if (g.gl == 0) r0 = atomicAdd(a.pack_rows, (unsigned long long)n);
+        r0 = g.bcast(r0, 0);
+        group_copy<G>(g, a.px + r0, Q.nx, n); group_copy<G>(g, a.py + r0, Q.ny, n); group_copy<G>(g, a.pth + r0, Q.nth, n);
+        group_copy<G>(g, a.pparent + r0, Q.parent, n);
+        if (a.pu && Q.uo) group_copy<G>(g, a.pu + 5 * r0, Q.uo, 5 * n);
+        if (g.gl == 0) a.row_start[q] = (long long)r0;
     }
 }
 
@@ -372,7 +413,8 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
     int k;
     for (k = 1; k < K; k++) {
         const int it = k - 1;
-        const int sx = __ldg(Q.sxy + 2 * it), sy = __ldg(Q.sxy + 2 * it + 1);
+        int sx, sy;
+        sample_xy(a, Q, it, sx, sy);
         const double qx = (double)sx, qy = (double)sy;
         const double qth = standardangle(__ldg(Q.sth + it));
         int code, near = -1, newi = -1;
@@ -600,7 +642,8 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         if (have) {
             const int my_it = k0 + g.gl;
             if (my_it < K - 1) {
-                const int sx = __ldg(Q.sxy + 2 * my_it), sy = __ldg(Q.sxy + 2 * my_it + 1);
+                int sx, sy;
+                sample_xy(a, Q, my_it, sx, sy);
                 qx = (double)sx; qy = (double)sy;
                 qth = standardangle(__ldg(Q.sth + my_it));
                 if (!Q.m.freespace(sx, sy)) pre = TRRT_IT_QRAND_BLOCKED; // rrt.py:148

@@ -52,6 +52,14 @@ class RrtResult:
     n_los: torch.Tensor | None = None
     counters: torch.Tensor | None = None
     lanes: int = 0
+    # packed copy of the rows that exist (rrt(..., pack=True)): rows row_start[q] ... + n_nodes[q] - 1 of the pack_* arrays
+    row_start: torch.Tensor | None = None
+    pack_total: torch.Tensor | None = None  # int64 [1]: rows in use
+    pack_x: torch.Tensor | None = None
+    pack_y: torch.Tensor | None = None
+    pack_theta: torch.Tensor | None = None
+    pack_parent: torch.Tensor | None = None
+    pack_u: torch.Tensor | None = None
 
     def host(self):
         return _host_dict(self)
@@ -99,7 +107,7 @@ class Planner:
                 t = t.to(dtype)
             t = t.contiguous()
         else:
-            npdt = {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}[dtype]
+            npdt = {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8, torch.int16: np.int16}[dtype]
             h = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=npdt)))
             t = h.pin_memory().to(self.device, non_blocking=True) if h.numel() else h.to(self.device)
         if shape is not None:
@@ -163,9 +171,12 @@ class Planner:
 
     # ------------------------------------------------------------------ K2
     def rrt(self, starts, goals, sample_xy, sample_th, K=None, params=None, map_id=None, logs=False, want_u=True,
-            counters=False, lanes=0, schedule=0, work_key="rrt", reuse=None):
+            counters=False, lanes=0, schedule=0, work_key="rrt", reuse=None, pack=False, packed=None):
         """rrt.rrt for a batch.  starts/goals float64 [q,3] (x, y, theta_deg); sample_xy int32 [q,K-1,2];
-        sample_th float64 [q,K-1].  K = builtins.K (node capacity; K-1 iterations)."""
+        sample_th float64 [q,K-1].  K = builtins.K (node capacity; K-1 iterations).
+        pack=True: the kernel also leaves a packed copy of the tree rows that exist (pack_x, pack_y, pack_theta,
+        pack_parent, pack_u; query q owns rows row_start[q] ... + n_nodes[q] - 1, pack_total rows in all); `packed` may
+        pass a dict of such arrays to use; its pack_total must then hold the first row to use (0 for arrays of this call's own)."""
         P = params or self.params
         with torch.cuda.device(self.device):
             starts = self._dev(starts, torch.float64).reshape(-1, 3)
@@ -178,7 +189,9 @@ class Planner:
             if sample_th.numel() != nq * (K - 1):
                 raise ValueError(f"sample stream has {sample_th.numel()} values, expected {nq} x (K-1 = {K - 1})")
             sample_th = sample_th.reshape(nq, K - 1)
-            sample_xy = self._dev(sample_xy, torch.int32).reshape(nq, K - 1, 2)
+            # int16 sample coordinates are taken as they are (half the host-to-device bytes of the stream's xy part)
+            xy16 = isinstance(sample_xy, torch.Tensor) and sample_xy.dtype == torch.int16
+            sample_xy = self._dev(sample_xy, torch.int16 if xy16 else torch.int32).reshape(nq, K - 1, 2)
             mid = self._map_ids(map_id, nq)
             dev = self.device
             f64 = dict(dtype=torch.float64, device=dev)
@@ -203,12 +216,24 @@ class Planner:
                     res.n_los = torch.empty(nq, **i32)
                 if counters:
                     res.counters = torch.zeros((nq, 8), dtype=torch.int64, device=dev)
+            if pack:
+                if packed is None:
+                    packed = {"pack_x": torch.empty(nq * K, **f64), "pack_y": torch.empty(nq * K, **f64),
+                              "pack_theta": torch.empty(nq * K, **f64), "pack_parent": torch.empty(nq * K, **i32),
+                              "row_start": torch.empty(nq, dtype=torch.int64, device=dev),
+                              "pack_total": torch.empty(1, dtype=torch.int64, device=dev)}
+                    if want_u:
+                        packed["pack_u"] = torch.empty((nq * K, 5), **f64)
+                    packed["pack_total"].zero_()
+                for k, v in packed.items():  # a reused set: the caller has set pack_total to the first row to use
+                    setattr(res, k, v)
             wb = self.lib.trrt_rrt_workspace_bytes(nq, K)
             work = self._scratch(work_key, wb)  # concurrent launches (rrt_host) must not share a workspace
             g = self.grid
             ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
             a = _lib.CRrtArgs(d_bits=g.bits.data_ptr(), n_maps=g.n_maps, H=g.H, W=g.W, d_map_id=ptr(mid),
                               params=P.to_c(), n_queries=nq, K=K, lanes_per_query=int(lanes), schedule=int(schedule),
+                              sample_xy_i16=int(xy16),
                               d_start=starts.data_ptr(), d_goal=goals.data_ptr(), d_sample_xy=sample_xy.data_ptr(),
                               d_sample_th=sample_th.data_ptr(), d_node_x=res.node_x.data_ptr(),
                               d_node_y=res.node_y.data_ptr(), d_node_th=res.node_theta.data_ptr(),
@@ -216,7 +241,12 @@ class Planner:
                               d_sol=res.sol.data_ptr(), d_status=res.status.data_ptr(), d_iters=res.iters.data_ptr(),
                               d_it_near=ptr(res.it_near), d_it_new=ptr(res.it_new), d_it_code=ptr(res.it_code),
                               d_los_log=ptr(res.los_log), d_n_los=ptr(res.n_los), d_counters=ptr(res.counters),
-                              d_work=work.data_ptr(), work_bytes=work.numel())
+                              d_work=work.data_ptr(), work_bytes=work.numel(),
+                              d_pack_rows=ptr(res.pack_total) if pack else None, d_row_start=ptr(res.row_start) if pack else None,
+                              d_pack_x=ptr(res.pack_x) if pack else None, d_pack_y=ptr(res.pack_y) if pack else None,
+                              d_pack_th=ptr(res.pack_theta) if pack else None,
+                              d_pack_parent=ptr(res.pack_parent) if pack else None,
+                              d_pack_u=ptr(res.pack_u) if (pack and want_u) else None)
             _lib.check(self.lib.trrt_rrt_batch(C.byref(a), self._stream()), "trrt_rrt_batch")
             res.lanes = int(lanes)
             # keep inputs alive until the stream has consumed them
@@ -224,30 +254,34 @@ class Planner:
         return res
 
     _TREE = ("node_x", "node_y", "node_theta", "parent", "u")
+    _PACKED = {"node_x": "pack_x", "node_y": "pack_y", "node_theta": "pack_theta", "parent": "pack_parent", "u": "pack_u"}
 
     def rrt_host(self, starts, goals, sample_xy, sample_th, out, K=None, chunks=4, wait=True, valid_rows_only=False, **kw):
         """rrt.rrt for a batch whose inputs and outputs live in (pinned) HOST memory: the queries are cut into
         `chunks` contiguous pieces, each on its own stream (host->device copy, fused kernel, device->host copy), so
         that the PCIe transfers of one piece overlap the planning of the others.  `out` maps RrtResult field names
         (node_x, node_y, node_theta, parent, u, n_nodes, sol, status, iters, ...) to host tensors with a leading
-        query dimension; they are filled in place.  The call returns after enqueuing.  With wait=True the planner's
+        query dimension; they are filled in place, and only the fields that are present travel (leave `u` out and the
+        kernel does not even produce it).  The call returns after enqueuing.  With wait=True the planner's
         current stream waits for every piece (synchronise it before reading `out`).  With wait=False nothing waits:
         successive calls queue piece c of the next batch behind piece c of this one on the same stream, so the
         transfers of one batch also overlap the planning of the next (double-buffered streaming of batches); call
         host_sync() before reading the outputs or reusing the host buffers.
 
         valid_rows_only=True: a tree holds n_nodes[q] <= K nodes (about half of K on cfg 3) and only those rows are
-        brought back.  The rows of every piece are packed on the device (trrt_rrt_pack_rows) and fetched with one
-        linear copy per array; in the host arrays (contiguous pinned tensors of the usual [q, K(, 5)] shape, viewed as
-        flat row arrays) the rows of query q are rows out["row_start"][q] ... + n_nodes[q] - 1, anything else is not
-        touched.  `out` must contain n_nodes and row_start (int64 [q]).  The size of a piece's copy is known once its
-        node count has reached the host, so the copies of a batch are issued one call later (or in host_sync()), on
-        copy streams of their own, while the next batch is already being planned into a second set of buffers."""
+        brought back.  The fused kernel itself packs them (one row reservation per finished query, trrt_rrt_args
+        d_pack_*), and every piece is fetched with one linear copy per array; in the host arrays (contiguous pinned
+        tensors of the usual [q, K(, 5)] shape, viewed as flat row arrays) the rows of query q are rows
+        out["row_start"][q] ... + n_nodes[q] - 1, anything else is not touched.  `out` must contain n_nodes and
+        row_start (int64 [q]).  The size of a piece's copy is known once its row count has reached the host, so the
+        copies of a batch are issued one call later (or in host_sync()), on copy streams of their own, while the next
+        batch is already being planned; the packed rows are double-buffered per piece."""
         ins = [t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))
                for t in (starts, goals, sample_xy, sample_th)]
         nq = ins[0].shape[0]
         chunks = max(1, min(int(chunks), nq))
         defer = bool(valid_rows_only)
+        want_u = "u" in out
         if defer:
             if "n_nodes" not in out or "row_start" not in out:
                 raise ValueError("valid_rows_only needs 'n_nodes' and 'row_start' among the outputs")
@@ -257,11 +291,38 @@ class Planner:
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
             if not hasattr(self, "_streams") or len(self._streams) < chunks:
+                self.host_sync()  # nothing may be in flight on streams that are about to be replaced
                 self._streams = [torch.cuda.Stream(self.device) for _ in range(chunks)]
-                # packing and fetching a finished piece must not queue behind the persistent kernels of the other pieces
-                self._copy_streams = [torch.cuda.Stream(self.device, priority=-1) for _ in range(chunks)]
+                self._copy_streams = [torch.cuda.Stream(self.device) for _ in range(chunks)]
             if not hasattr(self, "_host_cache"):
                 self._host_cache = {}
+            Kc = int(K) if K is not None else ins[3].numel() // nq + 1
+            pk = None
+            if defer:
+                # packed rows of the whole batch: two sets used alternately (one is fetched while the other is filled).  Piece c
+                # owns rows [lo*K, hi*K) of every array and its own row counter, which starts at lo*K, so the kernel's
+                # row_start values are positions in the batch-wide arrays -- and in the flat host arrays.  No small kernel
+                # runs between the pieces' persistent kernels (it would wait for an SM until one of them retires): the
+                # counters are initialised and read back by copies.
+                pkey = ("packed", nq, Kc, chunks, want_u)
+                pc = self._host_cache.get(pkey)
+                if pc is None:
+                    def new_set():
+                        d = {"pack_x": torch.empty(nq * Kc, dtype=torch.float64, device=self.device),
+                             "pack_y": torch.empty(nq * Kc, dtype=torch.float64, device=self.device),
+                             "pack_theta": torch.empty(nq * Kc, dtype=torch.float64, device=self.device),
+                             "pack_parent": torch.empty(nq * Kc, dtype=torch.int32, device=self.device),
+                             "row_start": torch.empty(nq, dtype=torch.int64, device=self.device),
+                             "pack_total": torch.empty(chunks, dtype=torch.int64, device=self.device),
+                             "total_host": torch.zeros(chunks, dtype=torch.int64).pin_memory(), "free": [None] * chunks}
+                        if want_u:
+                            d["pack_u"] = torch.empty((nq * Kc, 5), dtype=torch.float64, device=self.device)
+                        return d
+                    first = torch.tensor([nq * c // chunks * Kc for c in range(chunks)], dtype=torch.int64).pin_memory()
+                    pc = {"sets": [new_set(), new_set()], "turn": 0, "first": first}
+                    self._host_cache[pkey] = pc
+                pk = pc["sets"][pc["turn"]]
+                pc["turn"] = 1 - pc["turn"]
             start = torch.cuda.Event()
             start.record(main)
             keep, deferred = [], []
@@ -270,66 +331,44 @@ class Planner:
                 st = self._streams[c]
                 st.wait_event(start)
                 with torch.cuda.stream(st):
-                    # device buffers of a piece are allocated once and reused by later calls of the same shape; with
-                    # deferred tree copies there are two result sets per piece, used alternately
-                    key = (c, chunks, defer, tuple((tuple(t[lo:hi].shape), t.dtype) for t in ins))
+                    # device buffers of a piece are allocated once and reused by later calls of the same shape
+                    key = (c, chunks, want_u, tuple((tuple(t[lo:hi].shape), t.dtype) for t in ins))
                     cached = self._host_cache.get(key)
                     if cached is None:
-                        cached = {"din": [torch.empty(t[lo:hi].shape, dtype=t.dtype, device=self.device) for t in ins],
-                                  "res": [None, None], "free": [None, None], "turn": 0,
-                                  "total": [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)],
-                                  "packed": [None, None]}
+                        cached = {"din": [torch.empty(t[lo:hi].shape, dtype=t.dtype, device=self.device) for t in ins], "res": None}
                         self._host_cache[key] = cached
-                    turn = cached["turn"] if defer else 0
-                    cached["turn"] = 1 - turn if defer else 0
-                    if cached["free"][turn] is not None:
-                        st.wait_event(cached["free"][turn])  # the tree copies that still read this result set
-                        cached["free"][turn] = None
                     din = cached["din"]
                     for d, t in zip(din, ins):
                         d.copy_(t[lo:hi], non_blocking=True)
-                    res = self.rrt(*din, K=K, work_key=("rrt", c), reuse=cached["res"][turn], **kw)
-                    cached["res"][turn] = res
+                    packed = None
+                    if defer:
+                        if pk["free"][c] is not None:
+                            st.wait_event(pk["free"][c])  # the copies that still read this set's rows of the piece
+                            pk["free"][c] = None
+                        packed = {k: pk[k] for k in ("pack_x", "pack_y", "pack_theta", "pack_parent", "pack_u") if k in pk}
+                        packed["row_start"] = pk["row_start"][lo:hi]
+                        packed["pack_total"] = pk["pack_total"][c:c + 1]
+                        packed["pack_total"].copy_(pc["first"][c:c + 1], non_blocking=True)
+                    res = self.rrt(*din, K=K, work_key=("rrt", c), reuse=cached["res"], want_u=want_u, pack=defer, packed=packed, **kw)
+                    cached["res"] = res
                     for name, t in out.items():
-                        if defer and (name in self._TREE or name == "row_start"):
+                        if defer and name in self._TREE:
                             continue
                         t[lo:hi].copy_(getattr(res, name), non_blocking=True)
                     if defer:
-                        # pack the rows that exist, on the piece's (high-priority) copy stream; their number goes to a
-                        # host word that belongs to this result set
-                        planned = torch.cuda.Event()
-                        planned.record(st)
-                        cs = self._copy_streams[c]
-                        cs.wait_event(planned)
-                        with torch.cuda.stream(cs):
-                            n64 = res.n_nodes.to(torch.int64)
-                            ends = torch.cumsum(n64, 0)
-                            starts_ = ends - n64
-                            pk = cached["packed"][turn]
-                            if pk is None:
-                                pk = {k: torch.empty_like(getattr(res, k)) for k in self._TREE if getattr(res, k) is not None}
-                                cached["packed"][turn] = pk
-                            _lib.check(self.lib.trrt_rrt_pack_rows(
-                                hi - lo, res.K, res.n_nodes.data_ptr(), starts_.data_ptr(), res.node_x.data_ptr(),
-                                res.node_y.data_ptr(), res.node_theta.data_ptr(), res.parent.data_ptr(),
-                                res.u.data_ptr() if res.u is not None else None, pk["node_x"].data_ptr(), pk["node_y"].data_ptr(),
-                                pk["node_theta"].data_ptr(), pk["parent"].data_ptr(),
-                                pk["u"].data_ptr() if res.u is not None else None, cs.cuda_stream), "trrt_rrt_pack_rows")
-                            cached["total"][turn].copy_(ends[-1:], non_blocking=True)
-                            out["row_start"][lo:hi].copy_(starts_ + lo * res.K, non_blocking=True)
-                            keep.append((n64, ends, starts_))
+                        pk["total_host"][c:c + 1].copy_(res.pack_total, non_blocking=True)
                     keep.append((din, res))
                 done = torch.cuda.Event()
-                done.record(self._copy_streams[c] if defer else st)
+                done.record(st)
                 if defer:
-                    deferred.append((c, lo, hi, res, done, out, cached, turn))
+                    deferred.append((c, lo, hi, res.K, pk, done, out))
                 elif wait:
                     main.wait_event(done)
                 else:
                     self._pending = [e for e in getattr(self, "_pending", []) if not e.query()] + [done]
             self._inflight = keep  # tensors stay referenced until the next call
             if defer:
-                # the previous batch first (its n_nodes are on the host by now), this one only if the caller waits
+                # the previous batch first (its row counts are on the host by now), this one only if the caller waits
                 previous, self._deferred = getattr(self, "_deferred", []), deferred
                 self._issue_tree_copies(previous)
                 if wait:
@@ -341,20 +380,21 @@ class Planner:
     def _issue_tree_copies(self, items):
         """Second half of rrt_host(valid_rows_only=True) for the pieces in `items`: wait until the piece's row count is on
         the host, then fetch its packed rows with one linear copy per array on the piece's copy stream."""
-        for c, lo, hi, res, done, out, cached, turn in items:
+        for c, lo, hi, K, pk, done, out in items:
             done.synchronize()
-            total = min(max(int(cached["total"][turn]), 0), (hi - lo) * res.K)
+            rows = min(max(int(pk["total_host"][c]) - lo * K, 0), (hi - lo) * K)
             cs = self._copy_streams[c]
             cs.wait_event(done)
             with torch.cuda.stream(cs):
-                for name, src in cached["packed"][turn].items():
-                    if name not in out:
+                for name, pname in self._PACKED.items():
+                    if name not in out or pname not in pk:
                         continue
                     m = 5 if name == "u" else 1
-                    out[name].view(-1)[lo * res.K * m:lo * res.K * m + total * m].copy_(src.view(-1)[:total * m], non_blocking=True)
+                    sl = slice(lo * K * m, (lo * K + rows) * m)
+                    out[name].view(-1)[sl].copy_(pk[pname].view(-1)[sl], non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(cs)
-            cached["free"][turn] = copied
+            pk["free"][c] = copied
             self._pending = [e for e in getattr(self, "_pending", []) if not e.query()] + [copied]
 
     def host_sync(self):
