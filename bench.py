@@ -193,8 +193,10 @@ def physical_roofline(kernel, ms, bound, alg=None, note=""):
     r = {"kernel": kernel, "bound": bound, "achieved": None, "peak": None, "unit": None, "frac": None,
          "traffic": kc.get("dram_bytes"), "peak_source": "profiles/peaks.json (mb_peaks.cu on this pool's B200)",
          "counts_source": kc.get("source")}
-    if bound == "fp64" and kc.get("fp64_thread_inst") and pk.get("fp64_dadd_lane_inst_per_s"):
-        r.update(achieved=kc["fp64_thread_inst"] / sec / 1e12, peak=pk["fp64_dadd_lane_inst_per_s"] / 1e12, unit="T fp64 lane-inst/s")
+    if bound == "fp64" and kc.get("fp64_warp_inst") and pk.get("fp64_dadd_lane_inst_per_s"):
+        # a warp instruction occupies the pipe for all 32 lanes whatever its predicate mask: lane slots = warp instructions x 32
+        r.update(achieved=kc["fp64_warp_inst"] * 32 / sec / 1e12, peak=pk["fp64_dadd_lane_inst_per_s"] / 1e12, unit="T fp64 lane-slots/s",
+                 fp64_thread_inst_per_launch=kc.get("fp64_thread_inst"), fp64_warp_inst_per_launch=kc["fp64_warp_inst"])
     elif bound == "issue" and kc.get("warp_inst") and pk.get("issue_warp_inst_per_s_nominal"):
         r.update(achieved=kc["warp_inst"] / sec / 1e9, peak=pk["issue_warp_inst_per_s_nominal"] / 1e9, unit="G warp-inst/s")
     if r["achieved"] is not None:
@@ -445,7 +447,7 @@ def main():
                            "inserted node, over the measured HBM copy peak; NOT a physical HBM figure (trees are L1/L2/shared-memory "
                            "resident), kept for comparison with round 1"},
         note="bound by the fp64 pipe: the nearest scan issues 6 fp64-pipe instructions per (sample, node) pair and the steer / libm "
-             "chain is fp64 too; achieved = fp64 thread-instructions per launch (ncu, smsp__thread_inst_executed_pipe_fp64) / "
+             "chain is fp64 too; achieved = fp64-pipe warp instructions per launch x 32 (ncu, smsp__inst_executed_pipe_fp64) / "
              "CUDA-event time of this run, peak = DADD rate measured by mb_peaks.cu")
     if nq != NQ_PER_GPU or args.lanes or args.schedule:
         roofline["counts_note"] = "ncu counts were taken on the default cfg-3 launch; this run uses other options"

@@ -61,7 +61,8 @@ def main():
         p = Planner(OccupancyGrid(m2, device=dev))
         cells = np.argwhere(m2)
         rq = np.random.default_rng(5)
-        a, b = cells[rq.integers(len(cells), size=512)], cells[rq.integers(len(cells), size=512)]
+        nqt = int(sys.argv[2]) if len(sys.argv) > 2 else 8192  # the bench batch
+        a, b = cells[rq.integers(len(cells), size=nqt)], cells[rq.integers(len(cells), size=nqt)]
         sg = torch.from_numpy(np.stack([a[:, 1], a[:, 0], b[:, 1], b[:, 0]], 1).astype(np.int32)).to(dev)
         for _ in range(2):
             r = p.theta(sg, path_cap=64)
