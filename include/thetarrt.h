@@ -226,6 +226,23 @@ int trrt_arc_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
                    uint8_t *d_blocked, int lanes, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Pixel lists of the raster helpers, in the reference's list order, duplicates included:
+ *   mode 0  search.getArc(begin, land, u), curved edge    (search.py:144-182)
+ *   mode 1  search.bresenham(begin, land), also getArc of a straight u (search.py:43-94, :145-146)
+ *   mode 2  search.getCircle(center, r)                   (search.py:96-142; center = icc, r = rad)
+ * d_in [n][9] = begin x, y, land x, y, u.steer, icc x, icc y, rad, mode.
+ * d_pixels int32 [n][cap][2]; d_count int32 [n] = length of the full list, also when it exceeds cap (call again with a
+ * larger cap then).  Only the image shape is needed: getCircle filters by search.valid, not by occupancy.
+ *   trrt_clearance_batch  replaces rrt.bike_clear / rrt.front_of_bike_clear (rrt.py:208-222):
+ *       d_in [n][3] = x, y, theta -> d_clear uint8 [n][2]
+ *   trrt_anglediff_batch  replaces rrt.anglediff (rrt.py:108-115): d_in [n][2] = a1, a2 -> d_out [n]
+ * ------------------------------------------------------------------------- */
+int trrt_arc_pixels_batch(int H, int W, int64_t n, const double *d_in, int32_t cap, int32_t *d_pixels, int32_t *d_count, void *stream);
+int trrt_clearance_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32_t *d_map_id, const trrt_params *params,
+                         int64_t n, const double *d_in, uint8_t *d_clear, void *stream);
+int trrt_anglediff_batch(int64_t n, const double *d_in, double *d_out, void *stream);
+
+/* ---------------------------------------------------------------------------
  * rrt.findnearest (rrt.py:117-128): weighted xy+angle nearest over the child
  * entries of G.  Edges are given by the per-iteration log of trrt_rrt_batch
  * (parent = it_near, child = it_new); order of comparison = tree.keys() order
@@ -275,7 +292,9 @@ typedef struct trrt_theta_args {
     const int32_t *d_order;
 } trrt_theta_args;
 
-/* fills in n_slots / heap_cap when 0 and returns the bytes needed */
+/* fills in n_slots / heap_cap when 0 and returns the bytes needed: 256 + n_slots * (H*W + heap_cap) * 16, computed in
+   64 bits (default heap_cap = 2*H*W, so 48*H*W bytes per slot: cap n_slots by the memory you can spare before calling);
+   0 when the map cannot be planned (2*H*W does not fit an int32: TRRT_ERR_MAP_TOO_LARGE from trrt_theta_batch) */
 size_t trrt_theta_workspace_bytes(trrt_theta_args *args);
 int trrt_theta_batch(const trrt_theta_args *args, void *stream);
 

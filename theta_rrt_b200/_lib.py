@@ -86,6 +86,10 @@ SIGNATURES = {
     "trrt_drive_batch": (C.c_int, [C.POINTER(CParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "trrt_arc_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_void_p]),
+    "trrt_arc_pixels_batch": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "trrt_clearance_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(CParams), C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "trrt_anglediff_batch": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "trrt_findnearest_batch": (C.c_int, [C.POINTER(CParams), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),

@@ -6,10 +6,12 @@
 //   los_group_kernel<G>       same, G lanes per ray (optional)
 //   tile_grid_kernel / los_tiled_kernel  K4b: the same test, 8 pixels per step over 8x16-pixel strips, per-lane refill (trrt_los.cuh)
 //   nearest_tile_kernel   K1: fp64 argmin over SoA tree; query sets in registers, node slices per warp
-//   nearest_final_kernel      cross-slice reduction with lowest-index ties
+//                             (the last CTA of a query group folds the per-column partials, lowest-index ties)
 //   rrt_kernel_spec<G>    K2: fused rrt.rrt loop, speculative window of G iterations, persistent (trrt_rrt.cuh)
 //   rrt_kernel_coop<G>        same loop, G lanes cooperating on one iteration at a time
 //   steer / drive / arc batch kernels: single steps of K2 for the drop-in helpers and step-level parity tests
+//   arc_pixels_kernel         pixel lists of search.getArc / getCircle / bresenham in the reference's list order
+//   clearance / anglediff batch kernels: rrt.bike_clear, rrt.front_of_bike_clear, rrt.anglediff
 //   findnearest_kernel    rrt.findnearest over the edge log
 //   theta_kernel<G>       K3: A* / lazy Theta*, G lanes per query, G-ary heap
 //
@@ -19,7 +21,6 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/thetarrt.h"
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) los_group_kernel(const uint32_t *__restri
 //   in flight per lane.  With >= 8 query sets the warps of a CTA hold different sets and stream the same slice
 //   (reuse through L1); with fewer sets the spare warps split the CTA's slice, so that a single query still puts
 //   every warp of the GPU on the HBM stream.  Per-warp shuffle min-reduction ordered by (d2, index); partials go
-//   to the workspace and nearest_final_kernel folds them (one warp per query).
+//   to the workspace and the CTA that finishes last folds them (one warp per query).
 //   d2 = rn(rn(dx*dx) + rn(dy*dy)), dx = qx - x  (search.py:15 before the sqrt).
 // ===========================================================================
 #define NN_WARPS 8
@@ -195,7 +196,8 @@ __device__ __forceinline__ void nn_fold(const double (&qx)[TQ], const double (&q
 template <int TQ>
 __global__ void __launch_bounds__(NN_WARPS * 32) nearest_tile_kernel(const double *__restrict__ x, const double *__restrict__ y, int64_t n_nodes,
                                                                      const int32_t *__restrict__ qxy, int64_t n_q, int64_t slice_len, int spc_log2,
-                                                                     double *__restrict__ part_d, int32_t *__restrict__ part_i) {
+                                                                     double *part_d, int32_t *part_i, unsigned *done, int32_t *__restrict__ idx_out,
+                                                                     double *__restrict__ d2_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int spc = 1 << spc_log2, wps = NN_WARPS >> spc_log2; // query sets per CTA, warps per set
     const int set_in_cta = warp & (spc - 1), sub = warp >> spc_log2;
@@ -266,42 +268,37 @@ __global__ void __launch_bounds__(NN_WARPS * 32) nearest_tile_kernel(const doubl
         }
         part_d[(int64_t)blockIdx.y * n_q + q0 + lane] = d;
         part_i[(int64_t)blockIdx.y * n_q + q0 + lane] = i;
+        __threadfence(); // the partial is visible before this CTA is counted
     }
-}
-
-// one warp per query folds the per-slice partials; (d2, index) order makes the fold order irrelevant
-__global__ void __launch_bounds__(128) nearest_final_kernel(const double *__restrict__ part_d, const int32_t *__restrict__ part_i, int n_slices,
-                                                            int64_t n_q, int32_t *__restrict__ idx, double *__restrict__ d2) {
-    const int lane = threadIdx.x & 31;
-    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (q >= n_q) return;
-    double bd = INFINITY;
-    int bi = 0x7fffffff;
-    int s = lane;
-    for (; s + 96 < n_slices; s += 128) { // four independent loads in flight
-        double d0 = part_d[(int64_t)s * n_q + q], d1 = part_d[(int64_t)(s + 32) * n_q + q];
-        double d2_ = part_d[(int64_t)(s + 64) * n_q + q], d3 = part_d[(int64_t)(s + 96) * n_q + q];
-        int i0 = part_i[(int64_t)s * n_q + q], i1 = part_i[(int64_t)(s + 32) * n_q + q];
-        int i2 = part_i[(int64_t)(s + 64) * n_q + q], i3 = part_i[(int64_t)(s + 96) * n_q + q];
-        if (d0 < bd || (d0 == bd && i0 < bi)) { bd = d0; bi = i0; }
-        if (d1 < bd || (d1 == bd && i1 < bi)) { bd = d1; bi = i1; }
-        if (d2_ < bd || (d2_ == bd && i2 < bi)) { bd = d2_; bi = i2; }
-        if (d3 < bd || (d3 == bd && i3 < bi)) { bd = d3; bi = i3; }
-    }
-    for (; s < n_slices; s += 32) {
-        double d = part_d[(int64_t)s * n_q + q];
-        int i = part_i[(int64_t)s * n_q + q];
-        if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
-    }
+    // The CTA that finishes last among those sharing this query group folds the per-column partials (no second launch:
+    // a single-query scan is ~45 us, a launch plus a tiny kernel behind it ~10 us).  (d2, index) order makes the fold
+    // order irrelevant.
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(done + blockIdx.x, 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int n_slices = (int)gridDim.y;
+    const int64_t qa = (int64_t)blockIdx.x * spc * TQ;
+    for (int64_t q = qa + warp; q < qa + (int64_t)spc * TQ && q < n_q; q += NN_WARPS) {
+        double bd = INFINITY;
+        int bi = 0x7fffffff;
+        for (int sidx = lane; sidx < n_slices; sidx += 32) {
+            const double d = __ldcg(part_d + (int64_t)sidx * n_q + q);
+            const int i = __ldcg(part_i + (int64_t)sidx * n_q + q);
+            if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
+        }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double od = __shfl_xor_sync(0xffffffffu, bd, off);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-    }
-    if (lane == 0) {
-        idx[q] = (bi == 0x7fffffff) ? -1 : bi;
-        if (d2) d2[q] = bd;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) {
+            idx_out[q] = (bi == 0x7fffffff) ? -1 : bi;
+            if (d2_out) d2_out[q] = bd;
+        }
     }
 }
 
@@ -341,6 +338,125 @@ __global__ void arc_batch_kernel(const uint32_t *__restrict__ bits, int H, int W
     if (v[8] != 0.0) b = !los_group<G>(g, m, trunc_ll(v[0]), trunc_ll(v[1]), trunc_ll(v[2]), trunc_ll(v[3]));
     else b = arc_blocked<G>(g, m, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], nullptr, nullptr);
     if (g.gl == 0) blocked[i] = b ? 1 : 0;
+}
+
+// ===========================================================================
+// Pixel lists of the raster helpers, in the reference's own list order (duplicates included), one warp per item:
+//   mode 0  search.getArc(begin, land, u) for a curved edge        (search.py:144-182)
+//   mode 1  search.bresenham(begin, land) / getArc of a straight u (search.py:43-94, :145-146)
+//   mode 2  search.getCircle(center = icc, r = rad)                (search.py:96-142)
+// getCircle's loop emits, for y = 0 .. t_max, getCirclePoints(xc, yc, x_y, y): the offsets (v1, v2) with v1, v2 drawn in
+// order from [-p, p, -q, q] and |v1| != |v2|, i.e. (-p,-q) (-p,q) (p,-q) (p,q) (-q,-p) (-q,p) (q,-p) (q,p) -- for q = 0
+// that list holds every pixel twice, and so does the reference's.  Pixels outside the image are dropped (search.py:103),
+// then getArc keeps those inside the arc's angular span (arc_keeps_pixel).  Lane l of the warp owns row base + l; a warp
+// prefix sum of the rows' pixel counts gives every pixel its position in the list.
+// d_in [n][9] = begin x, y, land x, y, u.steer, icc x, icc y, rad, mode.  d_count[i] = length of the full list even when
+// it exceeds cap (the caller then calls again with a larger cap); d_pixels [n][cap][2].
+// ===========================================================================
+__global__ void __launch_bounds__(128) arc_pixels_kernel(int H, int W, int64_t n, const double *__restrict__ in, int cap,
+                                                         int32_t *__restrict__ pixels, int32_t *__restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (item >= n) return;
+    const double *v = in + 9 * item;
+    int32_t *out = pixels + item * (int64_t)cap * 2;
+    const int mode = (int)v[8];
+    long long total = 0;
+    auto emit = [&](int my_cnt, const int *px, const int *py) { // my_cnt pixels of this lane, lanes in order
+        int inc = my_cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const long long base = total + inc - my_cnt;
+        for (int k = 0; k < my_cnt; k++)
+            if (base + k < cap) { out[2 * (base + k)] = px[k]; out[2 * (base + k) + 1] = py[k]; }
+        total += __shfl_sync(0xffffffffu, inc, 31);
+    };
+    if (mode == 1) { // search.py:43-94
+        long long x0 = trunc_ll(v[0]), y0 = trunc_ll(v[1]), x1 = trunc_ll(v[2]), y1 = trunc_ll(v[3]);
+        const long long adx = llabs(x1 - x0), ady = llabs(y1 - y0);
+        const bool low = ady < adx;
+        if (low ? (x0 > x1) : (y0 > y1)) { long long t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+        const long long dmaj = low ? adx : ady, dmin = low ? ady : adx;
+        const long long step = low ? ((y1 < y0) ? -1 : 1) : ((x1 < x0) ? -1 : 1);
+        for (long long base = 0; base <= dmaj; base += 32) {
+            const long long i = base + lane;
+            int px[1], py[1], c = 0;
+            if (i <= dmaj) {
+                const long long sm = dmaj ? (2 * dmin * i + dmaj - 1) / (2 * dmaj) : 0;
+                px[0] = (int)(low ? x0 + i : x0 + step * sm);
+                py[0] = (int)(low ? y0 + step * sm : y0 + i);
+                c = 1;
+            }
+            emit(c, px, py);
+        }
+    } else {
+        Grid m;
+        m.W = W; m.H = H; m.wpr = 0; m.bits = nullptr;
+        const double bx = v[0], by = v[1], lx = v[2], ly = v[3];
+        const long long xc = trunc_ll(v[5]), yc = trunc_ll(v[6]), r = trunc_ll(v[7]);
+        ArcTest A;
+        A.iccx = v[5]; A.iccy = v[6]; A.usteer = v[4]; A.ready = false; A.literal_ready = false;
+        const long long tmax = circle_tmax(r);
+        for (long long base = 0; base <= tmax; base += 32) {
+            const long long t = base + lane;
+            int px[8], py[8], c = 0;
+            if (t <= tmax) {
+                const long long x = (t == 0) ? r : circle_x(r, t);
+                const long long o1[8] = {-x, -x, x, x, -t, -t, t, t}, o2[8] = {-t, t, -t, t, -x, x, -x, x};
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const long long qx = xc + o1[k], qy = yc + o2[k];
+                    if (!m.inb(qx, qy)) continue;
+                    if (mode == 0 && !arc_keeps_pixel(A, bx, by, lx, ly, qx, qy)) continue;
+                    px[c] = (int)qx; py[c] = (int)qy; c++;
+                }
+            }
+            emit(c, px, py);
+        }
+        // diagonal-gap pixels (search.py:124-138)
+        const long long rnd = py_round((double)r * 0.5 * sqrt(2.0));
+        bool drawmore = true;
+        {
+            const int nx[4] = {1, -1, 0, 0}, ny[4] = {0, 0, 1, -1};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const long long a = rnd + nx[i], b = rnd + ny[i];
+                if (m.inb(xc + a, yc + b) && circle_member(r, a, b)) drawmore = false;
+            }
+        }
+        if (drawmore) {
+            int px[1], py[1], c = 0;
+            if (lane < 4) { // (+,+) (-,-) (+,-) (-,+)
+                const long long qx = xc + ((lane == 0 || lane == 2) ? rnd : -rnd), qy = yc + ((lane == 0 || lane == 3) ? rnd : -rnd);
+                if (m.inb(qx, qy) && (mode != 0 || arc_keeps_pixel(A, bx, by, lx, ly, qx, qy))) { px[0] = (int)qx; py[0] = (int)qy; c = 1; }
+            }
+            emit(c, px, py);
+        }
+    }
+    if (lane == 0) count[item] = (int32_t)(total > 0x7fffffff ? 0x7fffffff : total);
+}
+
+// rrt.bike_clear / rrt.front_of_bike_clear (rrt.py:208-222) and rrt.anglediff (rrt.py:108-115) for batches:
+//   in [n][3] = x, y, theta  ->  clear [n][2] = bike_clear, front_of_bike_clear
+//   ang [n][2] = a1, a2      ->  diff [n]
+__global__ void clearance_batch_kernel(const uint32_t *__restrict__ bits, int H, int W, int wpr, const int32_t *__restrict__ map_id, BikeParams P,
+                                       int64_t n, const double *__restrict__ in, uint8_t *__restrict__ clear) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Grid m;
+    m.W = W; m.H = H; m.wpr = wpr;
+    m.bits = bits + (map_id ? (size_t)map_id[i] * H * wpr : 0);
+    const double x = in[3 * i], y = in[3 * i + 1], th = in[3 * i + 2];
+    const Rot R = rot_make(th);
+    double bx, by;
+    rot_apply(R, P.bikelength, 0.0, bx, by);
+    clear[2 * i] = los_lane(m, trunc_ll(x), trunc_ll(y), trunc_ll(bx + x), trunc_ll(by + y), nullptr) ? 1 : 0;
+    rot_apply(R, P.bikelength * P.frontclearance, 0.0, bx, by);
+    clear[2 * i + 1] = los_lane(m, trunc_ll(x), trunc_ll(y), trunc_ll(bx + x), trunc_ll(by + y), nullptr) ? 1 : 0;
+}
+__global__ void anglediff_batch_kernel(int64_t n, const double *__restrict__ in, double *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = anglediff(in[2 * i], in[2 * i + 1]);
 }
 
 // ===========================================================================
@@ -766,20 +882,19 @@ int trrt_los_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
     if (((uintptr_t)d_seg & 15) != 0) return TRRT_ERR_INVALID_ARGUMENT;
     // lanes per segment: 1 = one thread per ray (literal Bresenham).  Measured on the cfg-4 rays (2^20 rays of 1..512 px,
     // 88% blocked): 1 lane 232 us, 8 lanes 231 us, 16 lanes 208 us, 32 lanes 253 us; short clear rays (Theta*) favour 1.
-    int lanes = 1;
-    if (const char *e = getenv("TRRT_LOS_LANES")) lanes = atoi(e); // experiments only
+    // Experiment builds pick another width with -DTRRT_LOS_LANES=n; the library itself reads no environment.
+#ifndef TRRT_LOS_LANES
+#define TRRT_LOS_LANES 1
+#endif
     const int wpr = (W + 31) / 32;
     cudaStream_t st = (cudaStream_t)stream;
     const int4 *sg = (const int4 *)d_seg;
-    const unsigned blocks = (unsigned)((n * (lanes > 1 ? lanes : 1) + 255) / 256);
-    switch (lanes) {
-    case 2: los_group_kernel<2><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
-    case 4: los_group_kernel<4><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
-    case 8: los_group_kernel<8><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
-    case 16: los_group_kernel<16><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
-    case 32: los_group_kernel<32><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break;
-    default: los_batch_kernel<<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); break; // one thread per segment
-    }
+    const unsigned blocks = (unsigned)((n * TRRT_LOS_LANES + 255) / 256);
+#if TRRT_LOS_LANES > 1
+    los_group_kernel<TRRT_LOS_LANES><<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out);
+#else
+    los_batch_kernel<<<blocks, 256, 0, st>>>(d_bits, H, W, wpr, d_map_id, sg, n, d_out); // one thread per segment
+#endif
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }
@@ -814,18 +929,21 @@ int trrt_los_batch_tiled(const uint64_t *d_tiles, int n_maps, int H, int W, cons
     // 256 segments per warp when that still gives every SM 24 warps, never fewer than 64.  Measured on the cfg-4 rays:
     // rpw 96 .. 256 -> 73 .. 71 us; refill threshold 6 / 8 / 12 idle lanes -> 72.6 / 70.6 / 70.8 us; cooperative tail
     // from 4 / 8 / 16 remaining rays -> 72.4 / 70.6 / 70.7 us, without it 87 us.
-    int refill_min = 8, coop_max = 8;
+    // (experiment builds override these with -D; the library itself reads no environment)
+#ifndef TRRT_LOS_REFILL
+#define TRRT_LOS_REFILL 8
+#endif
+#ifndef TRRT_LOS_COOP
+#define TRRT_LOS_COOP 8
+#endif
+    const int refill_min = TRRT_LOS_REFILL, coop_max = TRRT_LOS_COOP;
     const long long target_warps = (long long)sm_count() * 24;
     long long rpw = ((n + target_warps - 1) / target_warps + 31) / 32 * 32;
     if (rpw < 64) rpw = 64;
     if (rpw > 256) rpw = 256;
-    if (const char *v = getenv("TRRT_LOS_RPW")) rpw = atoi(v);           // experiments only
-    if (const char *v = getenv("TRRT_LOS_REFILL")) refill_min = atoi(v); // experiments only
-    if (const char *v = getenv("TRRT_LOS_COOP")) coop_max = atoi(v);     // experiments only (0 = no cooperative tail)
-    if (rpw < 32) rpw = 32;
-    if (rpw > (1 << 30)) rpw = 1 << 30;
-    if (refill_min < 1) refill_min = 1;
-    if (refill_min > 32) refill_min = 32;
+#ifdef TRRT_LOS_RPW
+    rpw = TRRT_LOS_RPW;
+#endif
     const long long warps = (n + rpw - 1) / rpw;
     const unsigned blocks = (unsigned)((warps + TRRT_LOS_WARPS - 1) / TRRT_LOS_WARPS);
     los_tiled_kernel<<<blocks, TRRT_LOS_WARPS * 32, 0, (cudaStream_t)stream>>>((const uint4 *)d_tiles, H, (W + 7) / 8, d_map_id, (const int4 *)d_seg,
@@ -872,7 +990,8 @@ static NearestPlan nearest_plan(int64_t n_nodes, int64_t n_q) {
 size_t trrt_nearest_workspace_bytes(int64_t n_nodes, int64_t n_q) {
     if (n_nodes <= 0 || n_q <= 0) return 16;
     NearestPlan P = nearest_plan(n_nodes, n_q);
-    return (size_t)P.n_slices * (size_t)n_q * (sizeof(double) + sizeof(int32_t)) + 16;
+    // [partial d2 | partial index | one arrival counter per query group]
+    return (((size_t)P.n_slices * (size_t)n_q * (sizeof(double) + sizeof(int32_t)) + 15) & ~(size_t)15) + (size_t)P.grid_sets * sizeof(unsigned) + 16;
 }
 
 int trrt_nearest_batch(const double *d_x, const double *d_y, int64_t n_nodes, const int32_t *d_qxy, int64_t n_q, int32_t *d_idx,
@@ -891,15 +1010,15 @@ int trrt_nearest_batch(const double *d_x, const double *d_y, int64_t n_nodes, co
     const NearestPlan P = nearest_plan(n_nodes, n_q);
     double *part_d = (double *)d_work;
     int32_t *part_i = (int32_t *)(part_d + (size_t)P.n_slices * n_q);
+    unsigned *done = (unsigned *)((char *)d_work + (((size_t)P.n_slices * (size_t)n_q * (sizeof(double) + sizeof(int32_t)) + 15) & ~(size_t)15));
+    CUDA_TRY(cudaMemsetAsync(done, 0, (size_t)P.grid_sets * sizeof(unsigned), st));
     dim3 grid((unsigned)P.grid_sets, (unsigned)P.grid_cols);
     switch (P.tq) {
-    case 8: nearest_tile_kernel<8><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i); break;
-    case 4: nearest_tile_kernel<4><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i); break;
-    case 2: nearest_tile_kernel<2><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i); break;
-    default: nearest_tile_kernel<1><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i); break;
+    case 8: nearest_tile_kernel<8><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i, done, d_idx, d_d2); break;
+    case 4: nearest_tile_kernel<4><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i, done, d_idx, d_d2); break;
+    case 2: nearest_tile_kernel<2><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i, done, d_idx, d_d2); break;
+    default: nearest_tile_kernel<1><<<grid, NN_WARPS * 32, 0, st>>>(d_x, d_y, n_nodes, d_qxy, n_q, P.slice_len, P.spc_log2, part_d, part_i, done, d_idx, d_d2); break;
     }
-    CUDA_TRY(cudaGetLastError());
-    nearest_final_kernel<<<(unsigned)((n_q * 32 + 127) / 128), 128, 0, st>>>(part_d, part_i, P.n_slices, n_q, d_idx, d_d2);
     CUDA_TRY(cudaGetLastError());
     return TRRT_OK;
 }
@@ -1037,6 +1156,39 @@ int trrt_arc_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32
     return TRRT_OK;
 }
 
+int trrt_arc_pixels_batch(int H, int W, int64_t n, const double *d_in, int32_t cap, int32_t *d_pixels, int32_t *d_count, void *stream) {
+    int e = check_map(1, H, W);
+    if (e) return e;
+    if (n < 0 || cap < 0) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TRRT_OK;
+    if (!d_in || !d_count || (cap > 0 && !d_pixels)) return TRRT_ERR_INVALID_ARGUMENT;
+    arc_pixels_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(H, W, n, d_in, cap, d_pixels, d_count);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+int trrt_clearance_batch(const uint32_t *d_bits, int n_maps, int H, int W, const int32_t *d_map_id, const trrt_params *params, int64_t n,
+                         const double *d_in, uint8_t *d_clear, void *stream) {
+    int e = check_map(n_maps, H, W);
+    if (e) return e;
+    if (!params || n < 0) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TRRT_OK;
+    if (!d_bits || !d_in || !d_clear) return TRRT_ERR_INVALID_ARGUMENT;
+    clearance_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_bits, H, W, (W + 31) / 32, d_map_id, to_dev(*params), n,
+                                                                                         d_in, d_clear);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
+int trrt_anglediff_batch(int64_t n, const double *d_in, double *d_out, void *stream) {
+    if (n < 0) return TRRT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return TRRT_OK;
+    if (!d_in || !d_out) return TRRT_ERR_INVALID_ARGUMENT;
+    anglediff_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, d_in, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return TRRT_OK;
+}
+
 int trrt_findnearest_batch(const trrt_params *params, int64_t n_queries, int32_t K, const double *d_node_x, const double *d_node_y,
                            const double *d_node_th, const int32_t *d_n_nodes, const int32_t *d_it_near, const int32_t *d_it_new,
                            const double *d_goal, int32_t *d_best, double *d_best_dist, void *stream) {
@@ -1050,11 +1202,15 @@ int trrt_findnearest_batch(const trrt_params *params, int64_t n_queries, int32_t
     return TRRT_OK;
 }
 
-static void theta_plan(trrt_theta_args *A, int *G) {
+// Launch plan of theta_batch.  Everything is computed in 64 bits: a slot costs H*W cells of 16 B plus heap_cap entries of
+// 16 B (default 2*H*W, i.e. 48*H*W bytes per slot), so large maps times many slots reach hundreds of GB -- the caller caps
+// n_slots by the memory it can spare (Planner.theta does), and sizes that do not fit an int32 are refused.
+static int theta_plan(trrt_theta_args *A, int *G) {
     int g = A->lanes_per_query;
     if (g == 0) g = 32; // measured on map2: a full warp per search is fastest at every batch size (2048 queries: 96 / 163 / 215 ms for 32 / 16 / 8 lanes)
     if (g < 8) g = 8;
     *G = g;
+    if (A->H < 1 || A->W < 1) return TRRT_ERR_INVALID_ARGUMENT;
     if (A->n_slots <= 0) {
         // 16 warps per SM; 24 when the batch has more queries than that (measured on map2: 8192 queries 137 ms vs 152 ms)
         int wps = (A->n_queries * g > (int64_t)sm_count() * 16 * 32) ? 24 : 16;
@@ -1064,16 +1220,18 @@ static void theta_plan(trrt_theta_args *A, int *G) {
     if (A->heap_cap <= 0) {
         int64_t c = 2ll * A->H * A->W;
         if (c < 4096) c = 4096;
+        if (c > 0x7fffffffll) return TRRT_ERR_MAP_TOO_LARGE; // heap positions are int32
         A->heap_cap = (int32_t)c;
     }
+    return TRRT_OK;
 }
-static size_t theta_cells_bytes(const trrt_theta_args *A) { return (size_t)A->n_slots * A->H * A->W * sizeof(Cell); }
-static size_t theta_heap_bytes(const trrt_theta_args *A) { return (size_t)A->n_slots * A->heap_cap * sizeof(HeapEnt); }
+static size_t theta_cells_bytes(const trrt_theta_args *A) { return (size_t)A->n_slots * (size_t)A->H * (size_t)A->W * sizeof(Cell); }
+static size_t theta_heap_bytes(const trrt_theta_args *A) { return (size_t)A->n_slots * (size_t)A->heap_cap * sizeof(HeapEnt); }
 
 size_t trrt_theta_workspace_bytes(trrt_theta_args *args) {
     if (!args) return 0;
     int G;
-    theta_plan(args, &G);
+    if (theta_plan(args, &G) != TRRT_OK) return 0; // 0 = this map cannot be planned (trrt_theta_batch reports why)
     return 256 + theta_cells_bytes(args) + theta_heap_bytes(args);
 }
 
@@ -1089,7 +1247,8 @@ int trrt_theta_batch(const trrt_theta_args *args, void *stream) {
     if (A.d_los_log && (A.los_cap < 1 || !A.d_n_los)) return TRRT_ERR_INVALID_ARGUMENT;
     if ((uintptr_t)A.d_work & 15) return TRRT_ERR_INVALID_ARGUMENT;
     int G;
-    theta_plan(&A, &G);
+    e = theta_plan(&A, &G);
+    if (e) return e;
     if (G != 8 && G != 16 && G != 32) return TRRT_ERR_INVALID_ARGUMENT;
     size_t need = 256 + theta_cells_bytes(&A) + theta_heap_bytes(&A);
     if (A.work_bytes < need) return TRRT_ERR_WORKSPACE_TOO_SMALL;

@@ -465,12 +465,58 @@ class Planner:
                                                out.data_ptr(), int(lanes), self._stream()), "trrt_arc_batch")
         return out
 
+    def arc_pixels(self, inputs, cap=None):
+        """Pixel lists of search.getArc (mode 0), search.bresenham (mode 1) and search.getCircle (mode 2) in the reference's
+        list order, for rows (bx, by, lx, ly, u.steer, iccx, iccy, rad, mode).  Returns a list of int32 arrays [len, 2]."""
+        with torch.cuda.device(self.device):
+            inp = self._dev(inputs, torch.float64).reshape(-1, 9)
+            n = inp.shape[0]
+            g = self.grid
+            if cap is None:
+                cap = 16 * (g.H + g.W) + 64
+            while True:
+                pix = torch.empty((n, cap, 2), dtype=torch.int32, device=self.device)
+                cnt = torch.empty(n, dtype=torch.int32, device=self.device)
+                _lib.check(self.lib.trrt_arc_pixels_batch(g.H, g.W, n, inp.data_ptr(), int(cap), pix.data_ptr(), cnt.data_ptr(),
+                                                          self._stream()), "trrt_arc_pixels_batch")
+                c = cnt.cpu().numpy()
+                if n == 0 or int(c.max()) <= cap:
+                    break
+                cap = int(c.max())  # a list was longer than the buffer: once more with room for the longest
+            h = pix.cpu().numpy()
+        return [h[i, :int(c[i])].copy() for i in range(n)]
+
+    def clearance(self, nodes, map_id=None, params=None):
+        """rrt.bike_clear / rrt.front_of_bike_clear (rrt.py:208-222) for rows (x, y, theta).  Returns uint8 [n, 2]."""
+        P = params or self.params
+        with torch.cuda.device(self.device):
+            inp = self._dev(nodes, torch.float64).reshape(-1, 3)
+            n = inp.shape[0]
+            mid = self._map_ids(map_id, n)
+            out = torch.empty((n, 2), dtype=torch.uint8, device=self.device)
+            g = self.grid
+            cp = P.to_c()
+            _lib.check(self.lib.trrt_clearance_batch(g.bits.data_ptr(), g.n_maps, g.H, g.W, mid.data_ptr() if mid is not None else None,
+                                                     C.byref(cp), n, inp.data_ptr(), out.data_ptr(), self._stream()),
+                       "trrt_clearance_batch")
+        return out
+
+    def anglediff(self, pairs):
+        """rrt.anglediff (rrt.py:108-115) for rows (a1, a2) in degrees.  Returns float64 [n]."""
+        with torch.cuda.device(self.device):
+            inp = self._dev(pairs, torch.float64).reshape(-1, 2)
+            n = inp.shape[0]
+            out = torch.empty(n, dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.trrt_anglediff_batch(n, inp.data_ptr(), out.data_ptr(), self._stream()), "trrt_anglediff_batch")
+        return out
+
     # ------------------------------------------------------------------ K3
     def theta(self, start_goal, thetastar=None, map_id=None, path_cap=None, log_los=False, lanes=0, n_slots=0,
-              heap_cap=0, longest_first=True):
+              heap_cap=0, longest_first=True, mem_budget=None):
         """search.astar for queries int32 [q,4] = (sx, sy, gx, gy).  longest_first: dispatch the queries to the
         persistent slots by decreasing start-goal distance (a batch ends with its longest search; results stay
-        indexed by query)."""
+        indexed by query).  mem_budget: bytes the search workspace may take (default: half of the free device memory); the
+        number of concurrent searches is cut down to fit."""
         if thetastar is None:
             thetastar = self.params.THETASTAR
         with torch.cuda.device(self.device):
@@ -505,6 +551,17 @@ class Planner:
                 order = torch.argsort(d, descending=True).to(torch.int32)
                 a.d_order = order.data_ptr()
             wb = self.lib.trrt_theta_workspace_bytes(C.byref(a))  # fills n_slots / heap_cap
+            if wb == 0:
+                raise _lib.TrrtError("trrt_theta_batch: map too large for the search workspace (2*H*W heap entries must fit an int32)")
+            if mem_budget is None:  # half of what is free now plus what the cached workspace already holds
+                have = self._work.get("theta")
+                mem_budget = (torch.cuda.mem_get_info(self.device)[0] + (have.numel() if have is not None else 0)) // 2
+            if wb > mem_budget:  # fewer concurrent searches: a slot costs (H*W + heap_cap) * 16 bytes
+                per_slot = (g.H * g.W + int(a.heap_cap)) * 16
+                a.n_slots = max(1, int((mem_budget - 256) // per_slot))
+                wb = self.lib.trrt_theta_workspace_bytes(C.byref(a))
+                if wb > mem_budget:
+                    raise _lib.TrrtError(f"trrt_theta_batch: one search slot needs {per_slot} bytes, budget {mem_budget}")
             work = self._scratch("theta", wb)
             a.d_work = work.data_ptr()
             a.work_bytes = work.numel()

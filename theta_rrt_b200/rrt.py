@@ -55,6 +55,24 @@ def anglebetween(vec1, vec2):
     return standardangle(np.rad2deg(np.arctan2(det, dot)))
 
 
+def anglediff(angle1, angle2):
+    """rrt.py:108-115: wrapped angle2 - angle1 in degrees, through the device's quaternion evaluation."""
+    p = _context.current_planner()
+    return float(p.anglediff([[float(angle1), float(angle2)]]).cpu()[0])
+
+
+def bike_clear(node):
+    """rrt.py:208-213."""
+    p = _context.current_planner()
+    return bool(p.clearance([[node[0][0], node[0][1], node[1]]]).cpu()[0, 0])
+
+
+def front_of_bike_clear(node):
+    """rrt.py:215-222."""
+    p = _context.current_planner()
+    return bool(p.clearance([[node[0][0], node[0][1], node[1]]]).cpu()[0, 1])
+
+
 def rand_conf(mean):
     """rrt.py:53-68: one sample from numpy's global generator."""
     p = _context.current_planner()

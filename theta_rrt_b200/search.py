@@ -58,15 +58,99 @@ def freespace(node):
     return lineofsight(node, node)
 
 
-def astar_batch(queries, thetastar=None):
-    """search.astar for int queries [q,4] = (sx, sy, gx, gy).  Returns a ThetaResult on the host (dict of arrays)."""
+def bresenham(node1, node2):
+    """search.py:43-56 (with plotLineLow / plotLineHigh, :58-94): the pixel list, canonical start first."""
+    p = _context.current_planner()
+    row = [int(node1[0]), int(node1[1]), int(node2[0]), int(node2[1]), 0.0, 0.0, 0.0, 0.0, 1.0]
+    return [(int(x), int(y)) for x, y in p.arc_pixels([row])[0]]
+
+
+def getCirclePoints(xc, yc, p, q):
+    """search.py:96-105."""
+    pixels = []
+    for value1 in [-p, p, -q, q]:
+        for value2 in [-p, p, -q, q]:
+            if abs(value1) == abs(value2):
+                continue
+            pixel = (xc + value1, yc + value2)
+            if valid(pixel):
+                pixels.append(pixel)
+    return pixels
+
+
+def getCircle(center, r, draw=False):
+    """search.py:107-142: the in-bounds pixels of the midpoint circle (plus the diagonal-gap pixels), in the reference's
+    list order.  draw=True paints them into builtins.imarray like the reference does."""
+    p = _context.current_planner()
+    row = [0.0, 0.0, 0.0, 0.0, 0.0, float(center[0]), float(center[1]), float(r), 2.0]
+    pixels = [(int(x), int(y)) for x, y in p.arc_pixels([row])[0]]
+    if draw:
+        for item in pixels:
+            builtins.imarray[item[1], item[0]] = 0  # search.py:139-141
+    return pixels
+
+
+def getArc(begin, land, u):
+    """search.py:144-182: pixels of the edge (begin -> land) driven with control u = (steer, icc, rad, dist)."""
+    p = _context.current_planner()
+    if u[1] is None:  # search.py:145-146
+        return bresenham(begin, land)
+    row = [float(begin[0]), float(begin[1]), float(land[0]), float(land[1]), float(u[0]), float(u[1][0]), float(u[1][1]), float(u[2]), 0.0]
+    return [(int(x), int(y)) for x, y in p.arc_pixels([row])[0]]
+
+
+def getneighbors(node):
+    """search.py:184-194: the free 8-neighbours `node - delta`, delta in itertools.product([-1, 0, 1], repeat=2) order."""
+    cand = [(int(node[0]) - dx, int(node[1]) - dy) for dx in (-1, 0, 1) for dy in (-1, 0, 1) if (dx, dy) != (0, 0)]
+    free = lineofsight_batch([[c[0], c[1], c[0], c[1]] for c in cand])  # a zero-length ray is search.freespace
+    return [c for c, f in zip(cand, free) if f]
+
+
+def pathpixels(mainpath):
+    """The polyline rasterisation of search.drawpath (search.py:206-211): bresenham of consecutive waypoints, concatenated."""
+    pts = [q for q in mainpath if q is not None]
+    if len(pts) < 2:
+        return []
+    p = _context.current_planner()
+    rows = [[int(a[0]), int(a[1]), int(b[0]), int(b[1]), 0.0, 0.0, 0.0, 0.0, 1.0] for a, b in zip(pts, pts[1:])]
+    return [(int(x), int(y)) for seg in p.arc_pixels(rows) for x, y in seg]
+
+
+def drawpath(mainpath):
+    """search.py:206-219: rasterise the A* / Theta* path and scatter-plot it (only when matplotlib is installed; the
+    reference imports it unconditionally)."""
+    path = pathpixels(mainpath)
+    if path:
+        print("Found path")
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError:
+            return
+        xs = [item[0] for item in path]
+        ys = [item[1] for item in path]
+        plt.scatter(xs, ys, s=10, c=range(len(path)), cmap="winter")
+
+
+def astar_batch(queries, thetastar=None, path_cap=None):
+    """search.astar for int queries [q,4] = (sx, sy, gx, gy).  Returns a ThetaResult on the host (dict of arrays).
+    Paths are returned whole: the first pass stores up to path_cap nodes per query (default 4*(H+W), any-angle paths are
+    short), and the queries whose path is longer are searched once more with room for the longest."""
     p = _context.current_planner()
     if thetastar is None:
         thetastar = bool(getattr(builtins, "THETASTAR", True))
-    q = np.asarray(queries, dtype=np.int64).reshape(-1, 4)
+    q = np.asarray(queries, dtype=np.int64).reshape(-1, 4).astype(np.int32)
     H, W = p.grid.shape
-    res = p.theta(q.astype(np.int32), thetastar=thetastar, path_cap=H * W)
-    return res.host()
+    cap = int(path_cap) if path_cap else min(H * W, 4 * (H + W))
+    h = p.theta(q, thetastar=thetastar, path_cap=cap).host()
+    long_ = np.nonzero(h["path_len"] > cap)[0]
+    if len(long_):
+        cap2 = int(h["path_len"][long_].max())
+        h2 = p.theta(q[long_], thetastar=thetastar, path_cap=cap2).host()
+        path = np.full((len(q), cap2, 2), -1, np.int32)
+        path[:, :cap] = h["path"]
+        path[long_] = h2["path"]
+        h["path"] = path
+    return h
 
 
 def astar(start, goal):
