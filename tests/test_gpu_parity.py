@@ -275,6 +275,8 @@ def run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, schedule=0, **param
         assert np.array_equal(res["u"][q, :n].view(np.int64), o["u"].view(np.int64)), tag
         nl = int(res["n_los"][q])
         assert nl == o["n_los"] and np.array_equal(res["los_log"][q, :nl].astype(bool), o["los"]), tag
+    # no nearest decision where the reference's argmin over sqrt() could have kept a lower index than argmin(d2)
+    assert (res["counters"][:, 8] == 0).all(), (lanes, schedule)
     return res
 
 

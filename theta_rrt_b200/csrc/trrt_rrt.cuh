@@ -339,7 +339,34 @@ __device__ __forceinline__ void group_copy(const Group<G> &g, T *__restrict__ ds
 
 struct RrtCounters {
     unsigned long long scan, los, lospx, arcpx, arcang, steer, drive, probe;
+    unsigned long long ties; // nearest decisions that the reference's sqrt could have taken differently, see nearest_tie_audit
 };
+
+// The kernels take the argmin of d2 = rn(rn(dx*dx) + rn(dy*dy)); the reference takes np.argmin over sqrt(pow, pow)
+// (search.py:15, rrt.py:157), first minimum.  sqrt is monotone, so the two can only differ when a node with a LOWER index
+// than the winner has a d2 that is larger by a few ulp and collapses to the same rounded sqrt (then the reference keeps the
+// lower index).  Audit (counters mode only): is there a node i < winner with best < d2_i <= best * (1 + 2^-50)?
+// G lanes share the loop.  Expected: never -- the tests assert the counter is 0.
+template <int G>
+__device__ __forceinline__ bool nearest_tie_audit(const Group<G> &g, const double *__restrict__ nx, const double *__restrict__ ny, int winner,
+                                                  double best, double qx, double qy, bool shared_query) {
+    const double hi = best * (1.0 + 8.881784197001252e-16);
+    bool amb = false;
+    if (shared_query) { // the group works on ONE query: lanes stride the nodes
+        for (int i = g.gl; i < winner; i += G) {
+            const double dx = qx - nx[i], dy = qy - ny[i];
+            const double d = dx * dx + dy * dy;
+            if (d > best && d <= hi) amb = true;
+        }
+        return g.any(amb);
+    }
+    for (int i = 0; i < winner; i++) { // one query per lane (speculative window): every lane walks its own prefix
+        const double dx = qx - nx[i], dy = qy - ny[i];
+        const double d = dx * dx + dy * dy;
+        if (d > best && d <= hi) amb = true;
+    }
+    return amb;
+}
 
 template <int G>
 __device__ __forceinline__ void rrt_finish(const RrtDev &a, int64_t q, const Group<G> &g, const RrtQuery &Q, int K, int iters, int n, int sol,
@@ -359,8 +386,9 @@ __device__ __forceinline__ void rrt_finish(const RrtDev &a, int64_t q, const Gro
         a.iters[q] = iters;
         if (a.n_los) a.n_los[q] = nlos;
         if (a.counters) {
-            unsigned long long *o = a.counters + q * 8;
+            unsigned long long *o = a.counters + q * 9;
             o[0] = c.scan; o[1] = c.los; o[2] = c.lospx; o[3] = c.arcpx; o[4] = c.arcang; o[5] = c.steer; o[6] = c.drive; o[7] = c.probe;
+            o[8] = c.ties;
         }
     }
     if (a.row_start) { // packed copy of the rows that exist: one row reservation per query, coalesced copies by the group
@@ -408,7 +436,7 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
     const int K = a.K;
     RrtQuery Q;
     rrt_setup<G>(a, q, g, Q);
-    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0};
+    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND;
     int k;
     for (k = 1; k < K; k++) {
@@ -424,6 +452,10 @@ __global__ void __launch_bounds__(128) rrt_kernel_coop(const RrtDev a) {
         else {
             near = nearest_coop<G>(g, Q.nx, Q.ny, n, qx, qy);
             c.scan += (unsigned long long)n;
+            if (a.counters) {
+                const double bx_ = qx - Q.nx[near], by_ = qy - Q.ny[near];
+                if (nearest_tie_audit<G>(g, Q.nx, Q.ny, near, bx_ * bx_ + by_ * by_, qx, qy, true)) c.ties++;
+            }
             Expand e;
             expand_from<G>(g, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
             bool ins;
@@ -611,7 +643,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
     bool have = false, drained = false;
     int64_t q = 0;
     RrtQuery Q;
-    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0}; // lane-private sums, folded at the end
+    RrtCounters c = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // lane-private sums, folded at the end
     int n = 1, nlos = 0, sol = -1, status = TRRT_OK_NOT_FOUND, iters = 0, k0 = 0;
     TRRT_PROF(unsigned long long pf[24]; for (int i_ = 0; i_ < 24; i_++) pf[i_] = 0; long long t0_, t1_ = 0, t2_, t3_, t4_ = 0, t5_ = 0;)
     for (;;) {
@@ -623,7 +655,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
             else {
                 q = (int64_t)qq;
                 rrt_setup<G>(a, q, g, Q);
-                c = RrtCounters{0, 0, 0, 0, 0, 0, 0, 0};
+                c = RrtCounters{0, 0, 0, 0, 0, 0, 0, 0, 0};
                 n = 1; nlos = 0; sol = -1; status = TRRT_OK_NOT_FOUND; iters = 0; k0 = 0;
                 have = true;
             }
@@ -784,7 +816,10 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                 else {
                     near_j = near;
                     const int before = __popc(done & lane_lt); // nodes inserted by the earlier lanes of the window
-                    if (a.counters) { c.scan += (unsigned long long)(n + before); c.steer++; }
+                    if (a.counters) {
+                        c.scan += (unsigned long long)(n + before); c.steer++;
+                        if (nearest_tie_audit<1>(solo, Q.nx, Q.ny, near, bd, qx, qy, false)) c.ties++; // window nodes have higher indices
+                    }
                     if (e.code == TRRT_IT_STEER_CONSTRAINT) code = TRRT_IT_STEER_CONSTRAINT; // rrt.py:166
                     else {
                         if (Q.los_log) {
@@ -840,7 +875,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         if (finished || k0 >= K - 1) { // query finished
             if (a.counters) { // fold the lane-private counters
                 c.scan = g.sum(c.scan); c.los = g.sum(c.los); c.lospx = g.sum(c.lospx); c.arcpx = g.sum(c.arcpx); c.arcang = g.sum(c.arcang);
-                c.steer = g.sum(c.steer); c.drive = g.sum(c.drive); c.probe = g.sum(c.probe);
+                c.steer = g.sum(c.steer); c.drive = g.sum(c.drive); c.probe = g.sum(c.probe); c.ties = g.sum(c.ties);
             }
             rrt_finish<G>(a, q, g, Q, K, iters, n, sol, status, nlos, c);
             g.sync();

@@ -23,7 +23,7 @@ STATUS_NAMES = {0: "OK_FOUND", 1: "OK_NOT_FOUND", 2: "ERR_ENDPOINT_INVALID", 3: 
 IT_NEW_NODE, IT_EXISTING_NODE, IT_QRAND_BLOCKED, IT_QRAND_IN_TREE, IT_STEER_CONSTRAINT, IT_ARC_BLOCKED = range(6)
 IT_NOT_RUN = 255
 COUNTER_NAMES = ("nodes_scanned", "los_calls", "los_pixels", "arc_candidate_pixels", "arc_angle_tests",
-                 "steer_calls", "drive_calls", "hash_probes")
+                 "steer_calls", "drive_calls", "hash_probes", "nearest_sqrt_ties")
 
 
 def _host_dict(obj):
@@ -215,7 +215,7 @@ class Planner:
                     res.los_log = torch.zeros((nq, 2 * (K - 1)), dtype=torch.uint8, device=dev)
                     res.n_los = torch.empty(nq, **i32)
                 if counters:
-                    res.counters = torch.zeros((nq, 8), dtype=torch.int64, device=dev)
+                    res.counters = torch.zeros((nq, 9), dtype=torch.int64, device=dev)
             if pack:
                 if packed is None:
                     packed = {"pack_x": torch.empty(nq * K, **f64), "pack_y": torch.empty(nq * K, **f64),
