@@ -182,8 +182,8 @@ typedef struct trrt_rrt_args {
     uint8_t *d_los_log; /* [n_queries][2*(K-1)] search.lineofsight booleans in call order */
     int32_t *d_n_los;   /* [n_queries] */
     uint64_t *d_counters; /* [n_queries][9]: nodes scanned, los calls, los pixels, arc candidate pixels, arc angle tests, steer calls,
-                             drive calls, hash probes, nearest decisions with a lower-indexed runner-up within 4 ulp of the winner's
-                             squared distance (the only way argmin(d2) could differ from the reference's argmin(sqrt); expected 0);
+                             drive calls, hash probes, nearest decisions where a lower-indexed node has a larger squared distance with the
+                             SAME rounded sqrt (the only way argmin(d2) can differ from the reference's argmin(sqrt); expected 0);
                              may be NULL */
     /* scratch */
     void *d_work;

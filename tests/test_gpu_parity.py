@@ -350,6 +350,31 @@ def test_rrt_full_size_one_query_k5001(O, maps, lanes, schedule):
     run_rrt_pair(O, free, starts, goals, sxy, sth, K, lanes, schedule=schedule, tol_xy=0.0)
 
 
+def test_rrt_full_size_64_distinct_queries_k5001(O, maps):
+    """SURVEY 8(d) cfg 3: a >= 32-query subset at full depth.  64 DISTINCT cfg-3 queries (the bench workload's queries
+    1000..1063: same generator, same seeds), K = 5001, every tree bit for bit against the oracle (all host threads)."""
+    import os
+    import bench
+    free = maps["map1"]
+    nq, K, first = 64, 5001, 1000
+    starts, goals, sxy, sth = bench.make_rrt_workload(free, nq, K, first_query=first)
+    from oracle.c_oracle import Params as OP
+    o = O.rrt_batch(free, starts, goals, sxy, sth, K, OP(tol_xy=0.0), threads=os.cpu_count() or 1, want_nodes=True)
+    # the 64 queries ride in a batch large enough to fill the GPU's persistent CTAs (pooled scans, idle warps helping)
+    s2, g2, x2, t2 = (np.concatenate([a] * 48) for a in (starts, goals, sxy, sth))
+    res = planner_for(free, tol_xy=0.0).rrt(s2, g2, x2, t2, K=K, want_u=False).host()
+    assert int(o["iters"].sum()) > 200000 and (o["status"] == 4).sum() > 3  # full-length runs and early ends both present
+    for rep in (0, 17, 47):
+        sl = slice(rep * nq, (rep + 1) * nq)
+        for k in ("n_nodes", "status", "iters", "sol"):
+            assert np.array_equal(res[k][sl], o[k]), (k, rep)
+        for q in range(nq):
+            n = int(o["n_nodes"][q])
+            assert np.array_equal(res["parent"][sl][q, :n], o["parent"][q, :n]), (q, rep)
+            for j, k in enumerate(("node_x", "node_y", "node_theta")):
+                assert bits_equal(res[k][sl][q, :n], o["nodes"][q, :n, j]), (k, q, rep)
+
+
 @pytest.mark.parametrize("lanes,schedule", [(32, 0), (8, 0), (8, 1), (4, 0)])
 def test_rrt_goal_found_and_map2(O, maps, lanes, schedule):
     run = util.rrt_runs()[2]

@@ -344,26 +344,27 @@ struct RrtCounters {
 
 // The kernels take the argmin of d2 = rn(rn(dx*dx) + rn(dy*dy)); the reference takes np.argmin over sqrt(pow, pow)
 // (search.py:15, rrt.py:157), first minimum.  sqrt is monotone, so the two can only differ when a node with a LOWER index
-// than the winner has a d2 that is larger by a few ulp and collapses to the same rounded sqrt (then the reference keeps the
-// lower index).  Audit (counters mode only): is there a node i < winner with best < d2_i <= best * (1 + 2^-50)?
-// G lanes share the loop.  Expected: never -- the tests assert the counter is 0.
+// than the winner has a slightly larger d2 that collapses to the SAME correctly rounded sqrt (then the reference keeps the
+// lower index).  Audit (counters mode only): is there a node i < winner with d2_i > best and sqrt(d2_i) == sqrt(best)?
+// (Nodes a few ulp apart do occur -- the same point reached along two different arcs -- but their d2 differ by >= 2 ulp
+// and the square roots stay distinct.)  G lanes share the loop.  Expected: never -- the tests assert the counter is 0.
 template <int G>
 __device__ __forceinline__ bool nearest_tie_audit(const Group<G> &g, const double *__restrict__ nx, const double *__restrict__ ny, int winner,
                                                   double best, double qx, double qy, bool shared_query) {
-    const double hi = best * (1.0 + 8.881784197001252e-16);
+    const double hi = best * (1.0 + 8.881784197001252e-16), sbest = sqrt(best); // 4-ulp window first, the sqrt only inside it
     bool amb = false;
     if (shared_query) { // the group works on ONE query: lanes stride the nodes
         for (int i = g.gl; i < winner; i += G) {
             const double dx = qx - nx[i], dy = qy - ny[i];
             const double d = dx * dx + dy * dy;
-            if (d > best && d <= hi) amb = true;
+            if (d > best && d <= hi && sqrt(d) == sbest) amb = true;
         }
         return g.any(amb);
     }
     for (int i = 0; i < winner; i++) { // one query per lane (speculative window): every lane walks its own prefix
         const double dx = qx - nx[i], dy = qy - ny[i];
         const double d = dx * dx + dy * dy;
-        if (d > best && d <= hi) amb = true;
+        if (d > best && d <= hi && sqrt(d) == sbest) amb = true;
     }
     return amb;
 }
