@@ -555,11 +555,11 @@ def main():
         print(json.dumps(line), flush=True)
 
 
-def make_cfg5(rank, world):
+def make_cfg5(rank, world, nq5=32768, K5=1001):
     """BASELINE cfg 5: 65 536 queries = 32 768 RRT (as cfg 3, K = 1 001) + 32 768 Theta*, each bound to one of 64 random
     256 x 256 maps (4x4-block Bernoulli obstacles, p = 0.15, default_rng(7 + map)); this rank's contiguous shard."""
     from theta_rrt_b200 import samples, shard
-    n_maps5, side5, nq5, K5 = 64, 256, 32768, 1001
+    n_maps5, side5 = 64, 256
     maps5 = np.stack([synthetic_map(side5, 0.15, 4, 7 + m) for m in range(n_maps5)])
     r5 = np.random.default_rng(77)
     mid_r = r5.integers(0, n_maps5, nq5).astype(np.int32)
