@@ -1,2 +1,4 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "full_size_64 or rrt_batch_bitwise or cfg1" 2>&1 | tail -3
-python __graft_entry__.py smoke > gpurun_out/smoke_plain.log 2>&1 && timeout 900 compute-sanitizer --tool memcheck --log-file gpurun_out/sanitizer_memcheck_smoke.log python __graft_entry__.py smoke > gpurun_out/sanitizer_memcheck_stdout.log 2>&1; echo "memcheck rc=$?"; tail -5 gpurun_out/sanitizer_memcheck_smoke.log
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "rrt or cfg5 or cfg3 or steer" 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 --skip-secondary --skip-cpu > gpurun_out/b1.json 2> gpurun_out/b1.err; python -c "
+import json;d=json.loads(open('gpurun_out/b1.json').read().strip().splitlines()[-1]);print('ms',round(d['ms_per_step'],2),'Mexp/s',round(d['value']/1e6,1),'e2e',round(d['e2e']['value']/1e6,1), d['e2e']['ms_per_step'])"
+python profiles/tools/phase_prof.py > gpurun_out/phase1.txt 2>&1; cat gpurun_out/phase1.txt

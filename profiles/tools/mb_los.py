@@ -28,19 +28,12 @@ def run(label, **kw):
     print(f"{label}: {ms*1e3:8.1f} us  {len(seg)/ms/1e6:8.2f} G checks/s  same as first: {bool((res == ref).all())}", flush=True)
 
 
-for lanes in (1, 16):
-    os.environ["TRRT_LOS_LANES"] = str(lanes)
-    run(f"rows  lanes {lanes:2d}", layout="rows")
+run("rows  (one thread per ray)", layout="rows")
 run("tiles default", layout="tiles")
-for coop in (8, 16):
-    for rpw in (128, 256, 512):
-        for refill in (4, 8, 12):
-            os.environ["TRRT_LOS_RPW"] = str(rpw); os.environ["TRRT_LOS_REFILL"] = str(refill); os.environ["TRRT_LOS_COOP"] = str(coop)
-            run(f"tiles coop {coop:2d} rpw {rpw:4d} refill {refill:2d}", layout="tiles")
-os.environ.pop("TRRT_LOS_RPW"); os.environ.pop("TRRT_LOS_REFILL"); os.environ.pop("TRRT_LOS_COOP")
+# (the lanes / rays-per-warp / refill / cooperative-tail knobs are compile-time now: -DTRRT_LOS_LANES, -DTRRT_LOS_RPW,
+#  -DTRRT_LOS_REFILL, -DTRRT_LOS_COOP; build a variant with profiles/tools/variant_bench.py to sweep them)
 # sorted by length (what a caller could do for the rows kernel): upper bound on what refill can recover
 px = np.maximum(np.abs(seg[:, 2] - seg[:, 0]), np.abs(seg[:, 3] - seg[:, 1]))
 d_seg = torch.from_numpy(np.ascontiguousarray(seg[np.argsort(px)])).to(dev); ref = None
-os.environ["TRRT_LOS_LANES"] = "1"
 run("rows  lanes 1, rays sorted by length", layout="rows")
 run("tiles default, rays sorted by length", layout="tiles")
