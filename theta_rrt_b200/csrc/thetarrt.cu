@@ -694,9 +694,23 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                 const int cx = pk_x(cur), cy = pk_y(cur);
                 const int cur_i = cx * W + cy;
                 Cell cc = cells[cur_i];
+                // The records of the 8 neighbours are needed twice below (parent repair, relaxation) and nothing this group
+                // writes in between touches them, so lane j asks for neighbour j's record NOW: the loads (L2 most of the
+                // time: 1.4 MB of cells per search on map2) travel while the parent's line of sight is being walked.
+                bool nfree = false;
+                int nci = 0, nx_ = cx + ndx, ny_ = cy + ndy;
+                Cell nbp;
+                nbp.g = 0.0; nbp.parent = 0; nbp.stamp = 0u;
+                if (g.gl < 8 && m.inb(nx_, ny_)) {
+                    nci = nx_ * W + ny_;
+                    nbp = cells[nci];
+                    nfree = m.free_nb(nx_, ny_);
+                }
                 if (cc.stamp & 2u) continue; // already closed: stale heap copy (search.py:250-255); epoch matches by construction
+                double gpar = 0.0;
                 if (a.thetastar) { // search.py:258-263
                     const int px = pk_x((unsigned)cc.parent), py = pk_y((unsigned)cc.parent);
+                    gpar = cells[px * W + py].g; // g of the parent (search.py:295), asked for before the ray walk
                     bool los = los_group<G>(g, m, cx, cy, px, py);
                     if (los_log && lead && nlos < a.los_cap) los_log[nlos] = los ? 1 : 0;
                     nlos++;
@@ -704,13 +718,7 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                         double v = INFINITY;
                         int vi = 0x7fffffff;
                         unsigned vc = 0;
-                        if (g.gl < 8) {
-                            int x = cx + ndx, y = cy + ndy;
-                            if (m.freespace(x, y)) {
-                                Cell nb = cells[x * W + y];
-                                if ((nb.stamp >> 2) == epoch && (nb.stamp & 2u)) { v = nb.g + ndist; vi = j; vc = pk_of(x, y); }
-                            }
-                        }
+                        if (nfree && (nbp.stamp >> 2) == epoch && (nbp.stamp & 2u)) { v = nbp.g + ndist; vi = j; vc = pk_of(nx_, ny_); }
                         double bv = v;
                         int bj = vi;
                         g.min_di(bv, bj);
@@ -718,6 +726,7 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                         unsigned bc = g.bcast(vc, bj);
                         cc.parent = (int)bc;
                         cc.g = bv;
+                        gpar = g.bcast(nbp.g, bj); // the new parent is that closed neighbour
                     }
                 }
                 cc.stamp = (epoch << 2) | 2u; // openSet.remove, closedSet.add (search.py:265-266)
@@ -728,15 +737,14 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                 // neighbours (search.py:274-304), one lane each
                 const unsigned pcell = (unsigned)cc.parent;
                 const int ppx = pk_x(pcell), ppy = pk_y(pcell);
-                const double gpar = a.thetastar ? cells[ppx * W + ppy].g : 0.0;
                 int np_ = 0;
                 double f1 = 0, f2 = 0;
                 unsigned nbc = 0;
-                if (g.gl < 8) {
-                    int x = cx + ndx, y = cy + ndy;
-                    if (m.freespace(x, y)) {
-                        const int ci = x * W + y;
-                        Cell nb = cells[ci];
+                {
+                    const int x = nx_, y = ny_;
+                    if (nfree) {
+                        const int ci = nci;
+                        Cell nb = nbp;
                         bool mine = (nb.stamp >> 2) == epoch;
                         bool closed = mine && (nb.stamp & 2u);
                         if (!closed) {
