@@ -57,7 +57,11 @@ class OccupancyGrid:
                 st = torch.cuda.current_stream(self.device).cuda_stream
                 _lib.check(lib.trrt_tile_grid(self.bits.data_ptr(), self.n_maps, self.H, self.W, t.data_ptr(), st),
                            "trrt_tile_grid")
+                self._tiles_ready = torch.cuda.Event()
+                self._tiles_ready.record(torch.cuda.current_stream(self.device))
             self._tiles = t
+        else:  # built on some stream earlier: the caller's stream must not run ahead of that build
+            torch.cuda.current_stream(self.device).wait_event(self._tiles_ready)
         return self._tiles
 
     @property

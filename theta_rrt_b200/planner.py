@@ -115,7 +115,10 @@ class Planner:
         return t
 
     def _scratch(self, key, nbytes):
-        """Grow-only scratch buffers, one per kernel family (caller-owned workspace of the C ABI)."""
+        """Grow-only scratch buffers (caller-owned workspace of the C ABI), one per kernel family AND stream: calls issued on
+        different streams never share a workspace, and a buffer is only ever replaced by the stream that uses it (the caching
+        allocator hands a freed block back to the stream it was allocated on, behind the work already queued there)."""
+        key = (key, torch.cuda.current_stream(self.device).cuda_stream)
         cur = self._work.get(key)
         if cur is None or cur.numel() < nbytes:
             cur = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
@@ -554,7 +557,7 @@ class Planner:
             if wb == 0:
                 raise _lib.TrrtError("trrt_theta_batch: map too large for the search workspace (2*H*W heap entries must fit an int32)")
             if mem_budget is None:  # half of what is free now plus what the cached workspace already holds
-                have = self._work.get("theta")
+                have = self._work.get(("theta", torch.cuda.current_stream(self.device).cuda_stream))
                 mem_budget = (torch.cuda.mem_get_info(self.device)[0] + (have.numel() if have is not None else 0)) // 2
             if wb > mem_budget:  # fewer concurrent searches: a slot costs (H*W + heap_cap) * 16 bytes
                 per_slot = (g.H * g.W + int(a.heap_cap)) * 16

@@ -243,3 +243,42 @@ def edge_blocked(begin, land, u):
     row = [begin[0], begin[1], land[0], land[1], u[0], np.nan if straight else u[1][0], np.nan if straight else u[1][1],
            np.nan if straight else u[2], 1.0 if straight else 0.0]
     return bool(p.arc_blocked([row]).cpu()[0])
+
+
+# ---------------------------------------------------------------------------
+# visual adapters (rrt.py:16-40, 79-106, 224-270): display lists from theta_rrt_b200.draw, painted when matplotlib exists
+# ---------------------------------------------------------------------------
+def _draw_kw():
+    return dict(bikelength=float(getattr(builtins, "bikelength", 5)), forwardonly=bool(getattr(builtins, "FORWARDONLY", True)))
+
+
+def _paint(display_list):
+    from . import draw
+    try:
+        draw.render(display_list, ax=getattr(builtins, "ax", None), bikelength=_draw_kw()["bikelength"])
+    except ImportError:
+        pass  # no matplotlib: the display list is still returned
+    return display_list
+
+
+def draw_bicycle(bike_loc, theta, alpha, color='blue'):
+    """rrt.py:16-40."""
+    return _paint([("bike", (float(bike_loc[0]), float(bike_loc[1])), float(theta), float(alpha), color)])
+
+
+def draw_path_segment(bike1, bike2, u, colors=None, bikes=True):
+    """rrt.py:224-270."""
+    from . import draw
+    return _paint(draw.segment_primitives(bike1, bike2, u, colors=colors or draw.SEGMENT_COLORS, bikes=bikes, **_draw_kw()))
+
+
+def drawpath(solution, camefrom):
+    """rrt.py:79-98."""
+    from . import draw
+    return _paint(draw.path_display_list(solution, camefrom, **_draw_kw()))
+
+
+def drawtree(begin, graph, camefrom):
+    """rrt.py:100-106."""
+    from . import draw
+    return _paint(draw.tree_display_list(graph, camefrom, **_draw_kw()))
