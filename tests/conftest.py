@@ -10,7 +10,16 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def pytest_addoption(parser):
+    parser.addoption("--trrt-so", default=None, help="run against another build of libthetarrt.so (e.g. the checked build, "
+                                                    "profiles/tools/checked_build.sh)")
+
+
 def pytest_configure(config):
+    so = config.getoption("--trrt-so")
+    if so:
+        from theta_rrt_b200 import _lib
+        _lib.SO_PATH = os.path.abspath(so)
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "reference: needs the read-only reference tree at /root/reference")
 

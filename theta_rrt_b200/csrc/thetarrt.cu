@@ -565,6 +565,7 @@ template <int G>
 __device__ __forceinline__ bool heap_push(const Heap<G> &h, int &size, int cap, double f, unsigned c) {
     if (size >= cap) return false;
     int i = size++;
+    TRRT_CHECK(i >= 0 && i < cap);
     while (i > 0) {
         const int p = (i - 1) / G;
         double pf;
@@ -693,6 +694,7 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                 heap_pop<G>(g, heap, hsize, top_f, cur); // hsize stays uniform: every lane decrements its copy
                 const int cx = pk_x(cur), cy = pk_y(cur);
                 const int cur_i = cx * W + cy;
+                TRRT_CHECK(cx >= 0 && cx < H && cy >= 0 && cy < W && hsize >= 0 && hsize < a.heap_cap);
                 Cell cc = cells[cur_i];
                 // The records of the 8 neighbours are needed twice below (parent repair, relaxation) and nothing this group
                 // writes in between touches them, so lane j asks for neighbour j's record NOW: the loads (L2 most of the
@@ -703,6 +705,7 @@ __global__ void __launch_bounds__(128) theta_kernel(const ThetaDev a) {
                 nbp.g = 0.0; nbp.parent = 0; nbp.stamp = 0u;
                 if (g.gl < 8 && m.inb(nx_, ny_)) {
                     nci = nx_ * W + ny_;
+                    TRRT_CHECK(nci >= 0 && nci < H * W);
                     nbp = cells[nci];
                     nfree = m.free_nb(nx_, ny_);
                 }

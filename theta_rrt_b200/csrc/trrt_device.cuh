@@ -16,6 +16,17 @@
 
 #include "trrt_libm.h"
 
+// Bounds assertions of the checked build (-DTRRT_CHECKED, profiles/tools/checked_build.sh): every index the kernels derive
+// from data before a store -- node rows, log positions, partial-minimum slots, heap positions, pixel-list positions -- is
+// tested and a violation traps (the launch fails with an error instead of corrupting memory).  compute-sanitizer is closed
+// on this GPU pool, so the GPU test-suite is run once per round against this build instead (profiles/r2/NOTES.md).
+#ifdef TRRT_CHECKED
+#include <stdio.h>
+#define TRRT_CHECK(c) do { if (!(c)) { printf("TRRT_CHECK failed: %s (%s:%d)\n", #c, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define TRRT_CHECK(c) do { } while (0)
+#endif
+
 namespace trrt {
 
 // ---------------------------------------------------------------------------

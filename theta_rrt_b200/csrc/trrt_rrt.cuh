@@ -115,6 +115,7 @@ __device__ __forceinline__ void tree_insert_from(int32_t *tab, int tmask, int sl
 // the same for lanes of one warp inserting different keys at the same time (parallel segment commit)
 __device__ __forceinline__ void tree_insert_cas(int32_t *tab, int tmask, int slot, int idx) {
     unsigned s = (unsigned)slot;
+    TRRT_CHECK(slot >= 0 && slot <= tmask);
     while (atomicCAS(tab + s, 0, idx + 1) != 0) s = (s + 1) & (unsigned)tmask;
 }
 
@@ -302,6 +303,7 @@ __device__ __forceinline__ int rrt_insert(const Group<G> &g, const RrtQuery &Q, 
     if (idx < 0) {
         if (n >= K) { status = TRRT_ERR_CAPACITY; code = TRRT_IT_NOT_RUN; return -1; }
         idx = n++;
+        TRRT_CHECK(idx >= 1 && idx < K);
         inserted = true;
         if (g.gl == 0) {
             Q.nx[idx] = e.wx; Q.ny[idx] = e.wy; Q.nth[idx] = e.wth;
@@ -734,6 +736,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                     int pi = 0x7fffffff;
                     if (lo < hi) nearest_staged(scan_tile, pool_x[v], pool_y[v], lo, hi, sq.x, sq.y, pd, pi);
                     const int slot = b0 + (wid - k0v);
+                    TRRT_CHECK(slot >= 0 && slot < 2 * NW && lo >= 0 && hi <= n_v && v < NW);
                     pool_d[slot][lane] = pd; pool_i[slot][lane] = pi;
                 }
             }
@@ -750,6 +753,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
 #endif
         if (G == 32) { // fold the partial minima of this warp's tree, in node order: the first minimum wins
             const int lane = threadIdx.x & 31;
+            TRRT_CHECK(part0 >= 0 && part0 + nparts <= 2 * NW);
             for (int j = 0; j < nparts; j++) {
                 const double d = pool_d[part0 + j][lane];
                 if (d < bd) { bd = d; near = pool_i[part0 + j][lane]; }
@@ -757,6 +761,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         }
         // ---------------- phase A, part 2: everything after the nearest node
         if (live) {
+            TRRT_CHECK(near >= 0 && near < n);
             expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
             if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
         }
@@ -825,6 +830,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                     else {
                         if (Q.los_log) {
                             const int pos = nlos + __popc(m1 & lane_lt) + __popc(m2 & lane_lt);
+                            TRRT_CHECK(pos >= 0 && pos + nl <= 2 * (K - 1));
                             if (nl >= 1) Q.los_log[pos] = (e.flags >> 6) & 1;
                             if (nl >= 2) Q.los_log[pos + 1] = (e.flags >> 7) & 1;
                         }
@@ -834,6 +840,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                         else if (exist >= 0) { code = TRRT_IT_EXISTING_NODE; newi = exist; edge = newi != near; } // rrt.py:179 false
                         else { // rrt.py:179-180: a new vertex
                             newi = n + before;
+                            TRRT_CHECK(newi >= 1 && newi < K);
                             code = TRRT_IT_NEW_NODE;
                             edge = true; // its nearest node is an older one
                             Q.nx[newi] = e.wx; Q.ny[newi] = e.wy; Q.nth[newi] = e.wth;
@@ -842,6 +849,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
                     }
                 }
                 const int it = k0 + g.gl;
+                TRRT_CHECK(it >= 0 && it < K - 1);
                 if (Q.it_near) Q.it_near[it] = near_j;
                 if (Q.it_new) Q.it_new[it] = newi;
                 if (Q.it_code) Q.it_code[it] = (uint8_t)code;
