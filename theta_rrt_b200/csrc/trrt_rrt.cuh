@@ -1,6 +1,6 @@
 // trrt_rrt.cuh -- K2: the fused rrt.rrt loop (rrt.py:130-206), G lanes per query.
 //
-// Three schedules produce bit-identical results:
+// Two schedules produce bit-identical results:
 //
 //  * cooperative (schedule 1): the G lanes of a group work on ONE loop iteration at a time: the
 //    nearest scan, the Bresenham rays and the circle raster are lane-parallel, the scalar steer /
@@ -9,19 +9,15 @@
 //  * speculative window (schedule 0, default): the sample stream does not depend on the tree
 //    (rrt.py:144 draws before any test), and everything an iteration does after picking its
 //    nearest node depends only on (nearest node, sample, map).  So lane j of a group expands
-//    iteration k0+j against a SNAPSHOT of the tree (n0 nodes at the window start): the nearest
-//    scan (the warp stages the tree through shared memory once per window), steer, clearance rays,
-//    re-drive and edge raster.  The window is then committed in iteration order; every inserted
-//    node is broadcast so that later lanes can correct their snapshot winner (new nodes have
-//    higher indices, so the snapshot winner keeps ties) and their `in G` flags.  When a node of the
-//    window is strictly nearer (2.9% of the cfg-3 iterations) the iteration has to be expanded
-//    again from that node: the lanes this will happen to are predicted before the commit and
-//    expand together (phase A, part 3); what the prediction misses is expanded in lane-parallel
-//    rounds inside the commit.  The committed sequence is exactly the sequential loop.  One
+//    iteration k0+j against a SNAPSHOT of the tree: nearest scan (pooled over the warps of the CTA
+//    and staged through shared memory), steer, clearance rays, re-drive and edge raster.  The
+//    nodes the window would insert are then folded forward in iteration order (registers and
+//    shuffles): later lanes learn whether one of them is strictly nearer than their snapshot winner
+//    (new nodes have higher indices, so the snapshot winner keeps ties) and whether it equals their
+//    sample or their new node.  The window commits, in parallel, all lanes before the first one
+//    whose nearest node was inserted in this very window (24.6 of 32 on cfg 3), and the next window
+//    starts at that iteration.  The committed sequence is exactly the sequential loop.  One
 //    persistent kernel, groups pull queries from a counter.
-//
-//  * phase-split (schedule 2, experimental, trrt_wave.cuh): the same window as separate scan /
-//    expand / re-expand / commit kernels over all queries.
 #pragma once
 #include "trrt_bike.cuh"
 #include "trrt_lane.cuh"
