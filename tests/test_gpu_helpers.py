@@ -132,3 +132,25 @@ def test_dropin_helper_callables(O, maps):
     assert R.front_of_bike_clear(node) == O.lineofsight(free, (20, 20), (int(r10[0] + 20.5), int(r10[1] + 20.25)))
     assert R.anglediff(10.0, 350.0) == O.anglediff(10.0, 350.0)
     del builtins.imarray
+
+
+def test_device_libm_against_glibc_without_the_shared_header():
+    """The oracle shares csrc/trrt_libm.h with the device code, so a bug in that header would be invisible to the bitwise
+    CUDA-vs-oracle tests.  Here the DEVICE's sin / cos / atan2 (through rrt.anglediff's quaternion evaluation, rrt.py:108-115)
+    are compared with numpy / glibc, which know nothing of that header: same formula, 1e-12 degrees."""
+    from theta_rrt_b200 import OccupancyGrid, Planner
+    p = Planner(OccupancyGrid(np.ones((8, 8), bool)))
+    rng = np.random.default_rng(21)
+    a = np.concatenate([rng.uniform(-720, 720, size=(200000, 2)), rng.uniform(-1e-6, 1e-6, size=(1000, 2)),
+                        np.array([[0, 180], [180, 0], [90, -90], [-90, 90], [179.999999, -179.999999], [45, 45 + 1e-9]])])
+    got = p.anglediff(a).cpu().numpy()
+    h1, h2 = np.deg2rad(a[:, 0]) / 2, np.deg2rad(a[:, 1]) / 2
+    s1, c1, s2, c2 = np.sin(h1), np.cos(h1), np.sin(h2), np.cos(h2)
+    qz, qw = c1 * s2 - c2 * s1, c1 * c2 + s1 * s2          # q1^-1 * q2 about z
+    n = np.hypot(qz, qw)
+    ang = 2 * np.arctan2(qz / n, qw / n)
+    ang = np.where(ang < -np.pi, ang + 2 * np.pi, np.where(ang > np.pi, ang - 2 * np.pi, ang))
+    ref = np.rad2deg(ang)
+    d = np.abs(got - ref)
+    d = np.minimum(d, np.abs(d - 360))                     # +180 and -180 are the same angle
+    assert d.max() < 1e-12, d.max()
