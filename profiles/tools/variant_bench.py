@@ -28,6 +28,9 @@ def one(so, nq, K):
     import numpy as np, torch
     from theta_rrt_b200 import _lib
     _lib.SO_PATH = so
+    import ctypes
+    probe = ctypes.CDLL(so)  # older builds lack the newer entry points: bind only what the variant exports
+    _lib.SIGNATURES = {k: v for k, v in _lib.SIGNATURES.items() if hasattr(probe, k)}
     import bench
     from theta_rrt_b200 import OccupancyGrid, Params, Planner
     dev = torch.device("cuda:0")
@@ -58,8 +61,36 @@ def one(so, nq, K):
     print(f"{os.path.basename(so):28s} ms min {min(ms):7.2f} mean {sum(ms) / len(ms):7.2f}  iters {int(h['iters'].sum())} crc {crc:08x}", flush=True)
 
 
+def one_los(so):
+    """cfg-4 rays (2^20 on the 8192^2 grid) through the strip kernel of one build."""
+    import numpy as np, torch
+    from theta_rrt_b200 import _lib
+    _lib.SO_PATH = so
+    import bench
+    from theta_rrt_b200 import OccupancyGrid, Planner
+    dev = torch.device("cuda:0")
+    big = bench.synthetic_map(8192, 0.1, 8, 42)
+    pl = Planner(OccupancyGrid(big, device=dev))
+    seg = torch.from_numpy(bench.make_segments(big, 1 << 20, 7)).to(dev)
+    out = torch.empty(seg.shape[0], dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        pl.los(seg, out=out)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        pl.los(seg, out=out)
+    b.record(); torch.cuda.synchronize()
+    print(f"{os.path.basename(so):28s} los {a.elapsed_time(b) / 20 * 1e3:7.1f} us  visible {int(out.sum())} crc {zlib.crc32(out.cpu().numpy().tobytes()):08x}", flush=True)
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "build":
+    if sys.argv[1] == "one_los":
+        one_los(sys.argv[2])
+    elif sys.argv[1] == "los":
+        for n in sys.argv[2:]:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "one_los", os.path.join(VDIR, n + ".so")])
+    elif sys.argv[1] == "build":
         build(sys.argv[2], sys.argv[3:])
     elif sys.argv[1] == "one":
         one(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]))
