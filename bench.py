@@ -681,7 +681,14 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args, rank, world, di
                                                         "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 16 * n_big,
                                                         "peak_source": peak_src,
                                                         "note": "one query, 256 MiB SoA tree (> L2): every byte comes from HBM; the "
-                                                                "whole call (one kernel, last-CTA fold) is timed"}}
+                                                                "whole call (counter memset + one kernel with the last-CTA fold, "
+                                                                "launch gaps included) is timed"}}
+        ko = kernel_counts("nearest_tile_kernel_single_query")
+        if ko.get("ncu_duration_us"):
+            gbs = 16.0 * n_big / (ko["ncu_duration_us"] * 1e-6) / 1e9
+            out["nearest_single_query_hbm"]["kernel_only"] = {"us": ko["ncu_duration_us"], "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                                              "frac": gbs / peak, "source": ko.get("source"),
+                                                              "note": "device time of the kernel alone (ncu launch list of this bench command)"}
         del xb, yb, x, y
         if not args.skip_cpu:
             # CPU port (oracle) on a bounded sample of the same rays, all host threads

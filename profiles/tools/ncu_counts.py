@@ -36,6 +36,14 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "counts_*.csv"))):
         "ncu_fp64_pipe_active_pct": m.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
         "source": f"profiles/{tag}/counts_{name}.csv (ncu --metrics pass, profiles/tools/ncu_counts.sh)",
     }
+# the single-query nearest scan (256 MiB stream): device time of the kernel alone from the bench's ncu launch list
+ll = sorted(glob.glob(os.path.join(ROOT, "profiles", tag, "bench_launches_*.csv")))
+if ll:
+    d = [float(r[-1]) for r in csv.reader(open(ll[-1])) if len(r) > 14 and "nearest_tile_kernel<1>" in r[4] and r[-2] == "ns"]
+    if d:
+        d.sort()
+        out["nearest_tile_kernel_single_query"] = {"ncu_duration_us": d[len(d) // 2] / 1e3, "launches": len(d),
+                                                   "source": f"profiles/{tag}/{os.path.basename(ll[-1])} (gpu__time_duration, median)"}
 json.dump(out, open(os.path.join(ROOT, "profiles", "kernel_counts.json"), "w"), indent=1)
 for k, v in out.items():
     print(k, {a: b for a, b in v.items() if a != "source"})
