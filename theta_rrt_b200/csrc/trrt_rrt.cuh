@@ -601,6 +601,9 @@ __device__ __forceinline__ void nearest_staged(double2 *tile /* [2][2][TRRT_TILE
 // So the warps of a CTA enter the expansion together: one CTA barrier per window, placed after the (tiny-code)
 // nearest scan; the first warp through a code line fetches it for the others (SM i-cache hit rate 89%, gcc at 47%).
 // A CTA is TRRT_SPEC_THREADS wide.
+#ifndef TRRT_PARAMS_SMEM
+#define TRRT_PARAMS_SMEM 1 /* parameter block in shared memory instead of a per-thread stack copy: 1712 -> 1312 bytes of stack */
+#endif
 #ifndef TRRT_SPEC_LOCKSTEP
 #define TRRT_SPEC_LOCKSTEP 1
 #endif
@@ -637,6 +640,16 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
     __shared__ double pool_d[(G == 32) ? 2 * NW : 1][32];         // partial minima: one slot per (warp, tree) overlap
     __shared__ int pool_i[(G == 32) ? 2 * NW : 1][32];
     const unsigned lane_lt = (1u << g.gl) - 1u;
+#if TRRT_PARAMS_SMEM
+    // The parameter block is handed to non-inlined device functions by reference.  A reference into the kernel's parameter
+    // space would be copied to every thread's local stack (192 bytes); one copy per CTA in shared memory serves all of them.
+    __shared__ BikeParams sP;
+    for (int i = threadIdx.x; i < (int)(sizeof(BikeParams) / 4); i += blockDim.x) reinterpret_cast<int *>(&sP)[i] = reinterpret_cast<const int *>(&a.P)[i];
+    __syncthreads();
+#define TRRT_PARAMS_REF sP
+#else
+#define TRRT_PARAMS_REF a.P
+#endif
     // persistent groups: queries differ a lot in length (27% of the cfg-3 queries end early), so each group
     // pulls the next query from a counter instead of owning a fixed one.  One loop trip = one window.
     bool have = false, drained = false;
@@ -758,7 +771,7 @@ __global__ void __launch_bounds__(TRRT_SPEC_THREADS, TRRT_SPEC_BLOCKS_PER_SM) rr
         // ---------------- phase A, part 2: everything after the nearest node
         if (live) {
             TRRT_CHECK(near >= 0 && near < n);
-            expand_from<1>(solo, Q.m, a.P, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
+            expand_from<1>(solo, Q.m, TRRT_PARAMS_REF, Q.nx[near], Q.ny[near], Q.nth[near], qx, qy, qth, Q.gx, Q.gy, Q.gth, e);
             if (e.code == EX_ACCEPT) exist = tree_find_slot(Q.tab, Q.tmask, Q.nx, Q.ny, Q.nth, e.wx, e.wy, e.wth, probes, islot);
         }
         c.probe += probes;
