@@ -10,8 +10,10 @@
 
 namespace trrt {
 
+// The single-lane ray / raster functions are real calls; they take the grid BY VALUE (four words in registers): by reference the
+// caller's copy is forced into local memory (cfg 3: 35.2 -> 34.1 ms).
 // search.lineofsight (search.py:35-94) by one lane.  pixels (optional) += max(|dx|,|dy|)+1 for in-bounds rays.
-__device__ __noinline__ bool los_lane(const Grid &m, long long ax, long long ay, long long bx, long long by, int *pixels) {
+__device__ __noinline__ bool los_lane(const Grid m, long long ax, long long ay, long long bx, long long by, int *pixels) {
     if (!m.inb(ax, ay) || !m.inb(bx, by)) return false;
     int x0 = (int)ax, y0 = (int)ay, x1 = (int)bx, y1 = (int)by;
     const int adx = abs(x1 - x0), ady = abs(y1 - y0);
@@ -43,7 +45,7 @@ __device__ __forceinline__ int circle_x32(int c) {
 #define TRRT_LANE_RMAX 46000 /* r*r must fit 31 bits */
 
 // rrt.py:173-174 for a curved edge, one lane: is any pixel of getArc(begin, land, u) not free?
-__device__ __noinline__ bool arc_blocked_lane(const Grid &m, double bx, double by, double lx, double ly, double usteer, double iccx,
+__device__ __noinline__ bool arc_blocked_lane(const Grid m, double bx, double by, double lx, double ly, double usteer, double iccx,
                                               double iccy, double rad, int *cand_px, int *angle_tests) {
     const long long xc_ = trunc_ll(iccx), yc_ = trunc_ll(iccy), r_ = trunc_ll(rad);
     if (!(r_ < TRRT_LANE_RMAX)) { // enormous radius (cond() allows up to ~1e6): generic 64-bit raster
