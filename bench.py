@@ -706,7 +706,7 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args, rank, world, di
         m2 = maps["map2"]
         pt = Planner(OccupancyGrid(m2, device=dev))
         one = torch.tensor([[280, 0, 8, 280]], dtype=torch.int32, device=dev)
-        ms1 = timed0(lambda: pt.theta(one, lanes=32), n=3, warm=1)
+        ms1 = timed0(lambda: pt.theta(one, lanes=32), n=3, warm=2)
         r = pt.theta(one, lanes=32).host()
         out["theta_cfg2"] = {"metric": "theta_single_query_ms", "value": ms1, "unit": "ms", "expanded": int(r["expanded"][0]),
                              "los_checks": int(r["n_los"][0]), "cost": float(r["cost"][0]),
@@ -718,7 +718,7 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args, rank, world, di
         nqt = 8192
         a, b = cells[rq.integers(len(cells), size=nqt)], cells[rq.integers(len(cells), size=nqt)]
         sg = torch.from_numpy(np.stack([a[:, 1], a[:, 0], b[:, 1], b[:, 0]], 1).astype(np.int32)).to(dev)
-        msb = timed0(lambda: pt.theta(sg, path_cap=64), n=3, warm=1)
+        msb = timed0(lambda: pt.theta(sg, path_cap=64), n=3, warm=3)
         rb = pt.theta(sg, path_cap=64).host()
         out["theta_batch_map2"] = {"metric": "theta_expansions_per_sec", "value": float(rb["expanded"].sum()) / (msb / 1e3),
                                    "unit": "expansions/s", "ms": msb, "queries": nqt,
@@ -757,8 +757,10 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args, rank, world, di
 
     def step5t():
         res5["theta"] = p5.theta(sg5, map_id=dm_t, path_cap=64)
-    ms5r = max_over_ranks(torch, dist_on, dev, timed(step5r, n=3, warm=1))
-    ms5t = max_over_ranks(torch, dist_on, dev, timed(step5t, n=3, warm=1))
+    # (three warm-up calls: the result tensors of a call are freed when the next call's replace them, so the caching allocator
+    # needs two generations of them before the timed calls stop reaching cudaMalloc)
+    ms5r = max_over_ranks(torch, dist_on, dev, timed(step5r, n=3, warm=3))
+    ms5t = max_over_ranks(torch, dist_on, dev, timed(step5t, n=3, warm=3))
     it5, ex5, los5, found5 = sum_over_ranks(torch, dist_on, dev, [float(res5["rrt"].iters.sum()), float(res5["theta"].expanded.sum()),
                                                                   float(res5["theta"].n_los.sum()), float((res5["theta"].status == 0).sum())])
     ms5 = ms5r + ms5t
