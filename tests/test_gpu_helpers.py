@@ -154,3 +154,63 @@ def test_device_libm_against_glibc_without_the_shared_header():
     d = np.abs(got - ref)
     d = np.minimum(d, np.abs(d - 360))                     # +180 and -180 are the same angle
     assert d.max() < 1e-12, d.max()
+
+
+def test_int16_sample_coordinates_equal_int32(maps):
+    """trrt_rrt_args.sample_xy_i16: the same trees from int16 sample pairs (half the host-to-device bytes of that array)."""
+    import torch
+    from theta_rrt_b200 import samples
+    free = maps["map2"]  # 300 x 300: coordinates above 255
+    nq, K = 12, 301
+    starts, goals = util.random_queries(free, nq, 31)
+    sxy = np.empty((nq, K - 1, 2), np.int32); sth = np.empty((nq, K - 1))
+    for q in range(nq):
+        sxy[q], sth[q] = samples.make_stream(((goals[q, 0], goals[q, 1]), goals[q, 2]), K - 1, 900 + q, free.shape)
+    assert sxy.max() > 255
+    p = planner_for(free, tol_xy=0.0)
+    a = p.rrt(starts, goals, sxy, sth, K=K, logs=True).host()
+    for lanes, schedule in ((32, 0), (8, 0), (16, 1)):
+        b = p.rrt(starts, goals, torch.from_numpy(sxy.astype(np.int16)), sth, K=K, logs=True, lanes=lanes, schedule=schedule).host()
+        for k in ("n_nodes", "it_near", "it_code", "status", "iters"):
+            assert np.array_equal(a[k], b[k]), (k, lanes, schedule)
+        for q in range(nq):
+            n = int(a["n_nodes"][q])  # rows beyond n_nodes are not written
+            assert np.array_equal(a["parent"][q, :n], b["parent"][q, :n])
+            assert np.array_equal(a["node_x"][q, :n].view(np.int64), b["node_x"][q, :n].view(np.int64))
+
+
+def test_theta_memory_budget_cuts_the_slots_not_the_results(O, maps):
+    """Planner.theta(mem_budget=...): fewer concurrent searches, same answers; a budget below one slot is refused."""
+    from theta_rrt_b200 import _lib
+    free = maps["map1"]
+    p = planner_for(free)
+    rng = np.random.default_rng(4)
+    cells = np.argwhere(free)
+    a, b = cells[rng.integers(len(cells), size=200)], cells[rng.integers(len(cells), size=200)]
+    sg = np.stack([a[:, 1], a[:, 0], b[:, 1], b[:, 0]], 1).astype(np.int32)
+    full = p.theta(sg, path_cap=64)
+    per_slot = (100 * 100 + int(full.extra["heap_cap"])) * 16
+    small = p.theta(sg, path_cap=64, mem_budget=5 * per_slot + 256)
+    assert small.extra["n_slots"] == 5 < full.extra["n_slots"]
+    for k in ("path_len", "expanded", "status", "cost", "path"):
+        assert np.array_equal(full.host()[k], small.host()[k]), k
+    with pytest.raises(_lib.TrrtError):
+        p.theta(sg, mem_budget=per_slot // 2)
+
+
+def test_astar_batch_returns_long_paths_whole(O, maps):
+    """search.astar_batch: paths longer than the first pass's capacity are fetched by a second pass (A* mode: 86-node path)."""
+    from theta_rrt_b200 import search as S
+    builtins.imarray = maps["map1"]
+    builtins.THETASTAR = False
+    try:
+        q = [[5, 5, 90, 50], [2, 97, 97, 2], [5, 5, 6, 6]]
+        h = S.astar_batch(q, path_cap=16)
+        for i, (sx, sy, gx, gy) in enumerate(q):
+            o = O.astar(maps["map1"], (sx, sy), (gx, gy), thetastar=False)
+            n = int(h["path_len"][i])
+            assert n == len(o["path"]) and [tuple(v) for v in h["path"][i, :n].tolist()] == o["path"], i
+        assert h["path"].shape[1] >= 86
+    finally:
+        builtins.THETASTAR = True
+        del builtins.imarray
