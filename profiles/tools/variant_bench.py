@@ -84,9 +84,50 @@ def one_los(so):
     print(f"{os.path.basename(so):28s} los {a.elapsed_time(b) / 20 * 1e3:7.1f} us  visible {int(out.sum())} crc {zlib.crc32(out.cpu().numpy().tobytes()):08x}", flush=True)
 
 
+def one_theta(so):
+    """Theta* on map2: the single query of main.py:57 and the bench batch of 8 192 random free-cell queries."""
+    import numpy as np, torch
+    from theta_rrt_b200 import _lib
+    _lib.SO_PATH = so
+    import bench
+    from theta_rrt_b200 import OccupancyGrid, Planner
+    dev = torch.device("cuda:0")
+    m2 = bench.load_maps()["map2"]
+    pt = Planner(OccupancyGrid(m2, device=dev))
+    one_q = torch.tensor([[280, 0, 8, 280]], dtype=torch.int32, device=dev)
+    cells = np.argwhere(m2)
+    rq = np.random.default_rng(5)
+    a, b = cells[rq.integers(len(cells), size=8192)], cells[rq.integers(len(cells), size=8192)]
+    sg = torch.from_numpy(np.stack([a[:, 1], a[:, 0], b[:, 1], b[:, 0]], 1).astype(np.int32)).to(dev)
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x.record()
+        for _ in range(n):
+            fn()
+        y.record(); torch.cuda.synchronize()
+        return x.elapsed_time(y) / n
+    ms1 = timed(lambda: pt.theta(one_q, lanes=32), 3)
+    msb = timed(lambda: pt.theta(sg, path_cap=64), 3)
+    r = pt.theta(sg, path_cap=64).host()
+    crc = 0
+    for k in ("status", "expanded", "path_len", "cost", "n_los", "pushes", "path"):
+        if k in r and r[k] is not None:
+            crc = zlib.crc32(np.ascontiguousarray(r[k]).tobytes(), crc)
+    print(f"{os.path.basename(so):28s} theta single {ms1:7.2f} ms  batch {msb:7.2f} ms  {r['expanded'].sum() / msb / 1e3:6.1f} M exp/s  crc {crc:08x}", flush=True)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "one_los":
         one_los(sys.argv[2])
+    elif sys.argv[1] == "one_theta":
+        one_theta(sys.argv[2])
+    elif sys.argv[1] == "theta":
+        for n in sys.argv[2:]:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "one_theta", os.path.join(VDIR, n + ".so")])
     elif sys.argv[1] == "los":
         for n in sys.argv[2:]:
             subprocess.run([sys.executable, os.path.abspath(__file__), "one_los", os.path.join(VDIR, n + ".so")])
