@@ -29,9 +29,19 @@ buf = (ctypes.c_uint64 * 24)()
 for _ in range(2):
     p.rrt(*d, K=K)
 lib.trrt_debug_phase_prof(buf)
+nn = (ctypes.c_uint64 * 8)()
+if hasattr(lib, "trrt_debug_nn_stats"):
+    lib.trrt_debug_nn_stats.argtypes = [ctypes.c_void_p]
+    lib.trrt_debug_nn_stats(nn)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); r = p.rrt(*d, K=K); b.record(); torch.cuda.synchronize()
 lib.trrt_debug_phase_prof(buf)
+if hasattr(lib, "trrt_debug_nn_stats"):
+    lib.trrt_debug_nn_stats(nn)
+    s_ = [int(x) for x in nn]
+    if s_[0]:
+        print(f"cell-index lookups {s_[0]}: decided by the cells {100 * s_[1] / s_[0]:.1f}%, pages {s_[2] / s_[0]:.2f} nodes {s_[3] / s_[0]:.1f} per lookup; "
+              f"per warp-window {s_[5] / s_[4]:.2f} samples left to the full scan in {s_[6] / s_[4]:.2f} passes")
 v = [int(x) for x in buf]
 W = v[10]
 print(f"kernel {a.elapsed_time(b):.2f} ms, windows (warp x window) {W}, iterations {int(r.iters.sum())}")
@@ -47,6 +57,7 @@ for nm, i, j in names:
         var = v[j] * 1024 / Wn - mean * mean
         line += f"  std {max(var, 0) ** 0.5:9.0f}"
     print(line)
+if v[21]: print(f"  of 'sample, publish': nearest lookup {v[21] / WR:.0f} cycles, of which the walk over the cells {v[22] / WR:.0f}")
 post = (v[3] + v[7]) / W
 print(f"  after-barrier work per window: mean {post:.0f}, std {max(v[9] * 1024 / W - post * post, 0) ** 0.5:.0f}")
 print(f"  iterations committed per window: {v[17] / max(v[16], 1):.2f} of 32")
