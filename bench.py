@@ -727,6 +727,19 @@ def secondary_benchmarks(torch, dev, maps, peak, peak_src, args, rank, world, di
                                    "roofline": physical_roofline("theta_kernel", msb, "issue",
                                                                  note="latency-bound pointer chasing (heap, cells): issue slots are the "
                                                                       "nearest physical roof; the L1/L2 rates ride along")}
+        # The 8 192-query batch is bounded by its longest search (one warp, ~59 k expansions); four times the queries show
+        # what the kernel sustains when that tail is amortised.
+        nql = 4 * nqt
+        a, b = cells[rq.integers(len(cells), size=nql)], cells[rq.integers(len(cells), size=nql)]
+        sgl = torch.from_numpy(np.stack([a[:, 1], a[:, 0], b[:, 1], b[:, 0]], 1).astype(np.int32)).to(dev)
+        msl = timed0(lambda: pt.theta(sgl, path_cap=64), n=2, warm=2)
+        rl = pt.theta(sgl, path_cap=64)
+        out["theta_batch_map2"]["longest_search_expansions"] = int(rb["expanded"].max())
+        out["theta_batch_map2"]["large_batch"] = {"queries": nql, "ms": msl, "value": float(rl.expanded.sum()) / (msl / 1e3),
+                                                  "unit": "expansions/s", "longest_search_expansions": int(rl.expanded.max()),
+                                                  "note": "same kernel and map, 4x the queries: the batch above ends with its longest "
+                                                          "search running alone on one warp"}
+        del sgl, rl
         if not args.skip_cpu:
             from oracle import c_oracle as O
             nsmp = min(nqt, 4 * cores)
